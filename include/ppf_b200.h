@@ -1,0 +1,174 @@
+/* ppf_b200.h -- C ABI of libppf_b200.so: the Drost point-pair-feature recognition
+ * hot path of nicolasavru/objective-slam, rebuilt for NVIDIA B200 (sm_100a).
+ *
+ * Every entry point replaces one piece of the reference's C++/CUDA operator
+ * surface (paths relative to /root/reference/pcl/alignment):
+ *
+ *   ppf_registration          <- ppf_registration()              include/ppf.h:9-15, src/cuda/ppf.cu:29-106
+ *   ppf_scene_create          <- Scene::Scene()                   include/scene.h:14-16, src/cuda/scene.cu:24-55
+ *   ppf_scene_features        <- Scene::getModelPPFs/getHashKeys  include/scene.h:21-24 (debug/parity view)
+ *   ppf_model_create          <- Model::Model()                   include/model.h:17-19, src/cuda/model.cu:43-82
+ *   ppf_model_table_*         <- ParallelHashArray::Get*()        include/impl/parallel_hash_array.hpp:25-30
+ *   ppf_model_lookup          <- Model::ppf_lookup()              include/model.h:35, src/cuda/model.cu:269-306
+ *   ppf_lookup_vote           <- Model::ComputeUniqueVotes()      src/cuda/model.cu:95-171 (accumulate part)
+ *   ppf_lookup_finalize       <- Model::ComputeUniqueVotes()      src/cuda/model.cu:155-170 (threshold + order)
+ *   ppf_lookup_poses          <- Model::ComputeTransformations() + ComputeWeightedVoteCounts()
+ *                                                                 src/cuda/model.cu:173-200
+ *   ppf_lookup_cluster        <- Model::ClusterTransformations() + max_element
+ *                                                                 src/cuda/model.cu:202-244, 293-295
+ *   ppf_lookup_get            <- public members votes, voteCounts, transformations, transformation_trans,
+ *                                transformation_rots, vote_counts_out, max_idx   include/model.h:63-113
+ *
+ * Conventions: plain pointers and sizes only; every function returns a PPF_*
+ * status (never terminates the process, unlike HANDLE_ERROR, util.hpp:18-26);
+ * ppf_last_error() describes the last failure on the calling thread.  A handle
+ * must not be used from two host threads at once.  Work is issued on the CUDA
+ * device that is current when the handle is created.
+ *
+ * Clouds are given as two strided float arrays: point i has its position at
+ * xyz[i*xyz_stride + 0..2] and its normal at nrm[i*nrm_stride + 0..2] (strides in
+ * floats).  Dense N x 3 arrays use stride 3; an array of pcl::PointNormal (48 B:
+ * x y z _ nx ny nz _ curvature _ _ _) uses xyz=&p[0].x, nrm=&p[0].normal_x,
+ * stride 12 for both.  mem = PPF_MEM_HOST or PPF_MEM_DEVICE says where they live.
+ */
+#ifndef PPF_B200_H
+#define PPF_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    PPF_OK = 0,
+    PPF_ERR_INVALID = 1,      /* bad argument */
+    PPF_ERR_CUDA = 2,         /* CUDA runtime failure (see ppf_last_error) */
+    PPF_ERR_UNSUPPORTED = 3,  /* size outside the supported range */
+    PPF_ERR_NO_VOTES = 4      /* no scene pair matched the model: no pose */
+};
+
+enum { PPF_MEM_HOST = 0, PPF_MEM_DEVICE = 1 };
+
+#define PPF_N_ANGLE 30        /* kernel.h:15 */
+#define PPF_MAX_MODEL_POINTS 46340   /* N*N pair indices stay below 2^31, as in the reference */
+
+typedef struct ppf_scene ppf_scene_t;
+typedef struct ppf_model ppf_model_t;
+typedef struct ppf_lookup ppf_lookup_t;
+
+const char *ppf_last_error(void);
+const char *ppf_version(void);
+
+/* ---- Scene ------------------------------------------------------------------ */
+int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n,
+                     int mem, ppf_scene_t **out);
+void ppf_scene_destroy(ppf_scene_t *scene);
+int ppf_scene_num_points(const ppf_scene_t *scene);
+
+/* Quantised features (float4 per ordered pair) and 32-bit hash keys of the tile
+ * [ref_begin, ref_end) x [other_begin, other_end) of the scene's N x N pair matrix,
+ * exactly as ppf_kernel + ppf_hash_kernel (kernel.cu:404-477) would have stored
+ * them at out[ref*N + other]: rows with ref % ref_point_downsample_factor != 0 and
+ * self pairs hold (NaN,0,0,0) / key 0.  Outputs are host arrays of
+ * (ref_end-ref_begin)*(other_end-other_begin) elements; either may be NULL. */
+int ppf_scene_features(const ppf_scene_t *scene, float d_dist, unsigned ref_point_downsample_factor,
+                       int ref_begin, int ref_end, int other_begin, int other_end,
+                       float *ppfs_out, uint32_t *keys_out);
+
+/* ---- Model ------------------------------------------------------------------ */
+int ppf_model_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n,
+                     int mem, float d_dist, float vote_count_threshold, int use_l1_norm,
+                     int use_averaged_clusters, ppf_model_t **out);
+void ppf_model_destroy(ppf_model_t *model);
+int ppf_model_num_points(const ppf_model_t *model);
+
+/* ParallelHashArray contents: U unique sorted keys, counts, first index, and the
+ * N*N-long key-ordered map of pair indices (m_r*N + m_i).  size_t-typed like the
+ * reference's device_vector<std::size_t>. Any output may be NULL. */
+int ppf_model_table_sizes(const ppf_model_t *model, size_t *num_unique_keys, size_t *num_pairs);
+int ppf_model_table_get(const ppf_model_t *model, uint32_t *hashkeys, size_t *counts,
+                        size_t *first_index, size_t *key_to_pair);
+/* Model-side tile of quantised features / keys (same layout rules as ppf_scene_features, df = 1). */
+int ppf_model_features(const ppf_model_t *model, int ref_begin, int ref_end, int other_begin,
+                       int other_end, float *ppfs_out, uint32_t *keys_out);
+
+/* ---- Lookup (voting -> poses -> clustering) ------------------------------------- */
+typedef struct ppf_lookup_stats {
+    uint64_t num_scene_pairs;       /* R * N_s pairs processed by this call (the metric's unit)   */
+    uint64_t num_nonunique_votes;   /* model.cu:121-122 */
+    uint64_t num_unique_votes;      /* model.cu:152     */
+    uint32_t max_vote_count;        /* temp_votecounts[0], model.cu:160-164 */
+    uint32_t num_top_votes;         /* K, model.cu:165-170 */
+    uint32_t max_idx;               /* model.cu:293-295 */
+    uint32_t num_exact_alpha;       /* votes that took the exact-alpha path (diagnostic)          */
+    float    ms_vote, ms_finalize, ms_pose_cluster;   /* CUDA-event times of the last call        */
+} ppf_lookup_stats_t;
+
+int ppf_lookup_create(ppf_lookup_t **out);
+void ppf_lookup_destroy(ppf_lookup_t *lk);
+
+/* Whole Model::ppf_lookup: vote over every reference point s_r with
+ * s_r % ref_point_downsample_factor == 0, threshold, poses, clustering, argmax. */
+int ppf_model_lookup(const ppf_model_t *model, const ppf_scene_t *scene,
+                     unsigned ref_point_downsample_factor, ppf_lookup_t *lk);
+
+/* Staged form (what ppf_model_lookup runs, split so that several GPUs can share a
+ * scene).  shard_rank / shard_count select every shard_count-th reference point. */
+int ppf_lookup_vote(const ppf_model_t *model, const ppf_scene_t *scene,
+                    unsigned ref_point_downsample_factor, int shard_rank, int shard_count,
+                    ppf_lookup_t *lk);
+int ppf_lookup_local_max(const ppf_lookup_t *lk, uint32_t *max_count);
+/* Keep votes with count > vote_count_threshold * global_max, ordered (count desc, code asc). */
+int ppf_lookup_finalize(const ppf_model_t *model, uint32_t global_max, ppf_lookup_t *lk);
+/* Survivor list as device pointers (for NCCL allgather) and its replacement by a
+ * merged list (device pointers, K entries, already filtered; will be re-ordered). */
+int ppf_lookup_survivors(const ppf_lookup_t *lk, size_t *K, const uint64_t **codes_dev,
+                         const uint32_t **counts_dev);
+int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const uint32_t *counts_dev,
+                             size_t K);
+int ppf_lookup_poses(const ppf_model_t *model, const ppf_scene_t *scene, ppf_lookup_t *lk);
+int ppf_lookup_cluster(const ppf_model_t *model, ppf_lookup_t *lk);
+/* cpu_clustering = true variant: PCL-style greedy clustering of the survivors on one host
+ * core (transformation_clustering.cpp:62-137, model.cu:246-266); writes the best cluster's
+ * averaged pose (row-major 4x4) = cpu_transformations[0] of ppf.cu:75-77. */
+int ppf_lookup_cluster_cpu(const ppf_model_t *model, ppf_lookup_t *lk, float *pose_out);
+
+int ppf_lookup_get_stats(const ppf_lookup_t *lk, ppf_lookup_stats_t *stats);
+/* Host copies; K = stats.num_top_votes. votes/counts/weighted/scores: K; transformations: 16K
+ * (row-major 4x4); trans: 3K; rots: 4K (scalar part first); pose: 16 = rotation rows of
+ * transformations[max_idx] with translation transformation_trans[max_idx] (ppf.cu:80-93). */
+int ppf_lookup_get(const ppf_lookup_t *lk, uint64_t *votes, uint32_t *counts, float *transformations,
+                   float *weighted, float *trans, float *rots, float *scores, float *pose);
+/* Every non-zero accumulator cell (code, count), ascending code: the reference's
+ * unique votes before thresholding (model.cu:148-152). Needs vote_count_threshold = 0 semantics,
+ * so it re-runs the vote stage; meant for parity tests on small inputs. */
+int ppf_vote_histogram(const ppf_model_t *model, const ppf_scene_t *scene,
+                       unsigned ref_point_downsample_factor, uint64_t *codes_out,
+                       uint32_t *counts_out, size_t capacity, size_t *n_out);
+
+/* ---- The drop-in boundary -------------------------------------------------------- */
+typedef struct ppf_cloud {
+    const float *xyz; int xyz_stride;
+    const float *nrm; int nrm_stride;
+    int n;
+} ppf_cloud_t;
+
+/* ppf_registration (ppf.h:9-15): for every scene i and model j build Scene(scene_i, d_dist_j,
+ * df) and Model(model_j, d_dist_j, ...), run ppf_lookup and write the best model->scene pose to
+ * poses_out[(i*num_models + j)*16 ..] (row-major 4x4).  Host clouds in, host poses out.
+ * cpu_clustering selects the PCL-style greedy clustering (transformation_clustering.cpp:62-137).
+ * device follows the reference: the device used is min(device_count-1, device) (ppf.cu:45);
+ * model_weights is accepted and ignored, as in the reference (ppf.cu:35). status_out (optional,
+ * num_scenes*num_models) receives the per-pair status (PPF_ERR_NO_VOTES leaves a zero pose). */
+int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes, const ppf_cloud_t *model_clouds,
+                     int num_models, const float *model_d_dists,
+                     unsigned ref_point_downsample_factor, float vote_count_threshold,
+                     int cpu_clustering, int use_l1_norm, int use_averaged_clusters, int device,
+                     const float *model_weights, float *poses_out, int *status_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PPF_B200_H */

@@ -1,0 +1,416 @@
+// ppf_capi.cu -- the C ABI declared in include/ppf_b200.h (handles, error strings,
+// staging of the lookup stages, and the ppf_registration drop-in boundary).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/ppf_b200.h"
+#include "ppf_internal.cuh"
+
+namespace ppf {
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+}  // namespace ppf
+
+using namespace ppf;
+
+struct ppf_scene { Cloud cloud; };
+struct ppf_model { ModelTable table; };
+struct ppf_lookup {
+    VoteResult res;
+    ppf_lookup_stats_t stats;
+    int kernel_launches = 0;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+#define PPF_CHECK_ARG(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) { set_last_error(msg); return PPF_ERR_INVALID; } \
+    } while (0)
+
+int read_vote_scalars(ppf_lookup *lk) {
+    uint32_t h[4] = {0, 0, 0, 0};
+    unsigned long long t[2] = {0, 0};
+    if (lk->res.scalars) {
+        PPF_CUDA_TRY(cudaMemcpy(h, lk->res.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(cudaMemcpy(t, lk->res.votes_total, sizeof(t), cudaMemcpyDeviceToHost));
+    }
+    lk->stats.max_vote_count = h[1];
+    lk->stats.num_exact_alpha = h[3];
+    lk->stats.num_nonunique_votes = t[0];
+    lk->stats.num_unique_votes = t[1];
+    return PPF_OK;
+}
+}  // namespace
+
+extern "C" {
+
+const char *ppf_last_error(void) { return g_last_error.c_str(); }
+const char *ppf_version(void) { return "ppf_b200 0.1 (sm_100a)"; }
+
+// ---- Scene ------------------------------------------------------------------------
+int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem,
+                     ppf_scene_t **out) {
+    PPF_CHECK_ARG(out, "scene: out is NULL");
+    *out = nullptr;
+    ppf_scene *s = new ppf_scene();
+    int rc = cloud_create(xyz, xyz_stride, nrm, nrm_stride, n, mem, s->cloud);
+    if (rc) { cloud_free(s->cloud); delete s; return rc; }
+    *out = s;
+    return PPF_OK;
+}
+void ppf_scene_destroy(ppf_scene_t *s) {
+    if (!s) return;
+    cloud_free(s->cloud);
+    delete s;
+}
+int ppf_scene_num_points(const ppf_scene_t *s) { return s ? s->cloud.n : 0; }
+
+int ppf_scene_features(const ppf_scene_t *s, float d_dist, unsigned df, int rb, int re, int ob, int oe,
+                       float *ppfs_out, uint32_t *keys_out) {
+    PPF_CHECK_ARG(s, "scene is NULL");
+    return features_tile(s->cloud, d_dist, df, rb, re, ob, oe, ppfs_out, keys_out);
+}
+
+// ---- Model ------------------------------------------------------------------------
+int ppf_model_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem,
+                     float d_dist, float vote_count_threshold, int use_l1_norm, int use_averaged_clusters,
+                     ppf_model_t **out) {
+    PPF_CHECK_ARG(out, "model: out is NULL");
+    *out = nullptr;
+    ppf_model *m = new ppf_model();
+    m->table.d_dist = d_dist;
+    m->table.vote_count_threshold = vote_count_threshold;
+    m->table.use_l1_norm = use_l1_norm;
+    m->table.use_averaged_clusters = use_averaged_clusters;
+    int rc = cloud_create(xyz, xyz_stride, nrm, nrm_stride, n, mem, m->table.cloud);
+    if (!rc) rc = model_build(m->table);
+    if (rc) { model_free(m->table); delete m; return rc; }
+    *out = m;
+    return PPF_OK;
+}
+void ppf_model_destroy(ppf_model_t *m) {
+    if (!m) return;
+    model_free(m->table);
+    delete m;
+}
+int ppf_model_num_points(const ppf_model_t *m) { return m ? m->table.cloud.n : 0; }
+
+int ppf_model_table_sizes(const ppf_model_t *m, size_t *U, size_t *npairs) {
+    PPF_CHECK_ARG(m, "model is NULL");
+    if (U) *U = m->table.U;
+    if (npairs) *npairs = (size_t)m->table.cloud.n * m->table.cloud.n;
+    return PPF_OK;
+}
+int ppf_model_table_get(const ppf_model_t *m, uint32_t *hashkeys, size_t *counts, size_t *first, size_t *map) {
+    PPF_CHECK_ARG(m, "model is NULL");
+    return model_table_get(m->table, hashkeys, counts, first, map);
+}
+int ppf_model_features(const ppf_model_t *m, int rb, int re, int ob, int oe, float *ppfs_out, uint32_t *keys_out) {
+    PPF_CHECK_ARG(m, "model is NULL");
+    return features_tile(m->table.cloud, m->table.d_dist, 1, rb, re, ob, oe, ppfs_out, keys_out);
+}
+
+// ---- Lookup -----------------------------------------------------------------------
+int ppf_lookup_create(ppf_lookup_t **out) {
+    PPF_CHECK_ARG(out, "lookup: out is NULL");
+    ppf_lookup *lk = new ppf_lookup();
+    std::memset(&lk->stats, 0, sizeof(lk->stats));
+    for (auto &e : lk->ev)
+        if (cudaEventCreate(&e) != cudaSuccess) { set_last_error("cudaEventCreate failed"); delete lk; return PPF_ERR_CUDA; }
+    *out = lk;
+    return PPF_OK;
+}
+void ppf_lookup_destroy(ppf_lookup_t *lk) {
+    if (!lk) return;
+    vote_result_free(lk->res);
+    for (auto &e : lk->ev) if (e) cudaEventDestroy(e);
+    delete lk;
+}
+
+int ppf_lookup_vote(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, int shard_rank, int shard_count,
+                    ppf_lookup_t *lk) {
+    PPF_CHECK_ARG(m && s && lk, "vote: NULL handle");
+    std::memset(&lk->stats, 0, sizeof(lk->stats));
+    unsigned long long pairs = 0;
+    cudaEventRecord(lk->ev[0], 0);
+    int rc = vote_run(m->table, s->cloud, df, shard_rank, shard_count, 0, lk->res, &pairs, &lk->kernel_launches);
+    cudaEventRecord(lk->ev[1], 0);
+    if (rc) return rc;
+    PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[1]));
+    cudaEventElapsedTime(&lk->stats.ms_vote, lk->ev[0], lk->ev[1]);
+    lk->stats.num_scene_pairs = pairs;
+    return read_vote_scalars(lk);
+}
+
+int ppf_lookup_local_max(const ppf_lookup_t *lk, uint32_t *max_count) {
+    PPF_CHECK_ARG(lk && max_count, "local_max: NULL argument");
+    *max_count = lk->stats.max_vote_count;
+    return PPF_OK;
+}
+
+int ppf_lookup_finalize(const ppf_model_t *m, uint32_t global_max, ppf_lookup_t *lk) {
+    PPF_CHECK_ARG(m && lk, "finalize: NULL handle");
+    cudaEventRecord(lk->ev[1], 0);
+    int rc = vote_finalize(m->table, global_max, 0, lk->res);
+    cudaEventRecord(lk->ev[2], 0);
+    if (rc) return rc;
+    PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[2]));
+    cudaEventElapsedTime(&lk->stats.ms_finalize, lk->ev[1], lk->ev[2]);
+    lk->stats.max_vote_count = global_max;
+    lk->stats.num_top_votes = (uint32_t)lk->res.K;
+    return PPF_OK;
+}
+
+int ppf_lookup_survivors(const ppf_lookup_t *lk, size_t *K, const uint64_t **codes_dev, const uint32_t **counts_dev) {
+    PPF_CHECK_ARG(lk && K, "survivors: NULL argument");
+    *K = lk->res.K;
+    if (codes_dev) *codes_dev = (const uint64_t *)lk->res.codes;
+    if (counts_dev) *counts_dev = lk->res.counts;
+    return PPF_OK;
+}
+
+int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const uint32_t *counts_dev, size_t K) {
+    PPF_CHECK_ARG(lk && (K == 0 || (codes_dev && counts_dev)), "set_survivors: NULL argument");
+    unsigned long long *c = nullptr; uint32_t *n = nullptr;
+    if (K) {
+        PPF_CUDA_TRY(cudaMalloc(&c, K * 8));
+        PPF_CUDA_TRY(cudaMalloc(&n, K * 4));
+        PPF_CUDA_TRY(cudaMemcpy(c, codes_dev, K * 8, cudaMemcpyDeviceToDevice));
+        PPF_CUDA_TRY(cudaMemcpy(n, counts_dev, K * 4, cudaMemcpyDeviceToDevice));
+    }
+    int rc = order_survivors(lk->res, K, c, n);
+    cudaFree(c); cudaFree(n);
+    lk->stats.num_top_votes = (uint32_t)lk->res.K;
+    return rc;
+}
+
+int ppf_lookup_poses(const ppf_model_t *m, const ppf_scene_t *s, ppf_lookup_t *lk) {
+    PPF_CHECK_ARG(m && s && lk, "poses: NULL handle");
+    cudaEventRecord(lk->ev[2], 0);
+    return poses_run(m->table, s->cloud, lk->res);
+}
+
+int ppf_lookup_cluster(const ppf_model_t *m, ppf_lookup_t *lk) {
+    PPF_CHECK_ARG(m && lk, "cluster: NULL handle");
+    int rc = cluster_run(m->table, lk->res);
+    cudaEventRecord(lk->ev[3], 0);
+    if (rc) return rc;
+    PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[3]));
+    cudaEventElapsedTime(&lk->stats.ms_pose_cluster, lk->ev[2], lk->ev[3]);
+    lk->stats.max_idx = lk->res.max_idx;
+    return PPF_OK;
+}
+
+int ppf_model_lookup(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk) {
+    int rc = ppf_lookup_vote(m, s, df, 0, 1, lk);
+    if (rc) return rc;
+    if ((rc = ppf_lookup_finalize(m, lk->stats.max_vote_count, lk))) return rc;
+    if ((rc = ppf_lookup_poses(m, s, lk))) return rc;
+    if ((rc = ppf_lookup_cluster(m, lk))) return rc;
+    if (lk->stats.num_nonunique_votes == 0) { set_last_error("lookup: no scene pair matched the model"); return PPF_ERR_NO_VOTES; }
+    return PPF_OK;
+}
+
+int ppf_lookup_get_stats(const ppf_lookup_t *lk, ppf_lookup_stats_t *stats) {
+    PPF_CHECK_ARG(lk && stats, "stats: NULL argument");
+    *stats = lk->stats;
+    return PPF_OK;
+}
+
+int ppf_lookup_get(const ppf_lookup_t *lk, uint64_t *votes, uint32_t *counts, float *transformations,
+                   float *weighted, float *trans, float *rots, float *scores, float *pose) {
+    PPF_CHECK_ARG(lk, "get: NULL handle");
+    const VoteResult &r = lk->res;
+    size_t K = r.K;
+    if (pose) std::memset(pose, 0, 16 * sizeof(float));
+    if (K == 0) return PPF_OK;
+    if (votes) PPF_CUDA_TRY(cudaMemcpy(votes, r.codes, K * 8, cudaMemcpyDeviceToHost));
+    if (counts) PPF_CUDA_TRY(cudaMemcpy(counts, r.counts, K * 4, cudaMemcpyDeviceToHost));
+    if (transformations) PPF_CUDA_TRY(cudaMemcpy(transformations, r.transformations, K * 64, cudaMemcpyDeviceToHost));
+    if (weighted) PPF_CUDA_TRY(cudaMemcpy(weighted, r.weighted, K * 4, cudaMemcpyDeviceToHost));
+    if (trans) PPF_CUDA_TRY(cudaMemcpy(trans, r.trans, K * 12, cudaMemcpyDeviceToHost));
+    if (rots) PPF_CUDA_TRY(cudaMemcpy(rots, r.rots, K * 16, cudaMemcpyDeviceToHost));
+    if (scores) PPF_CUDA_TRY(cudaMemcpy(scores, r.scores, K * 4, cudaMemcpyDeviceToHost));
+    if (pose) {
+        // ppf.cu:80-93 -- only the winning pose crosses the bus (the reference copies all K)
+        float t[3];
+        PPF_CUDA_TRY(cudaMemcpy(pose, r.transformations + (size_t)r.max_idx * 16, 64, cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(cudaMemcpy(t, r.trans + r.max_idx, 12, cudaMemcpyDeviceToHost));
+        pose[3] = t[0]; pose[7] = t[1]; pose[11] = t[2];
+    }
+    return PPF_OK;
+}
+
+int ppf_vote_histogram(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, uint64_t *codes_out,
+                       uint32_t *counts_out, size_t capacity, size_t *n_out) {
+    PPF_CHECK_ARG(m && s && n_out, "histogram: NULL argument");
+    VoteResult r;
+    int rc = vote_run(m->table, s->cloud, df, 0, 1, 1, r, nullptr, nullptr);
+    uint32_t h[4] = {0, 0, 0, 0};
+    if (!rc && r.scalars) {
+        if (cudaMemcpy(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) rc = PPF_ERR_CUDA;
+    }
+    if (!rc) {
+        // ascending code order == the order thrust::sort + histogram() leaves (model.cu:148-151)
+        *n_out = h[0];
+        if (h[0] && codes_out && counts_out && h[0] <= capacity) {
+            std::vector<unsigned long long> c(h[0]);
+            std::vector<uint32_t> n(h[0]);
+            cudaMemcpy(c.data(), r.cand_codes, (size_t)h[0] * 8, cudaMemcpyDeviceToHost);
+            cudaMemcpy(n.data(), r.cand_counts, (size_t)h[0] * 4, cudaMemcpyDeviceToHost);
+            std::vector<uint32_t> order(h[0]);
+            for (uint32_t i = 0; i < h[0]; i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return c[a] < c[b]; });
+            for (uint32_t i = 0; i < h[0]; i++) { codes_out[i] = c[order[i]]; counts_out[i] = n[order[i]]; }
+        }
+    }
+    vote_result_free(r);
+    return rc;
+}
+
+}  // extern "C"
+
+// ---- PCL-style greedy pose clustering on the host (cpu_clustering = true) ----------------
+// Follows clusterPoses / posesWithinErrorBounds (transformation_clustering.cpp:62-137) and
+// Model::ClusterTransformationsCPU (model.cu:246-266).  K is 10^2..10^5 and the algorithm
+// is inherently sequential (a pose joins the first cluster whose SEED is close), so it
+// runs on one host core exactly like the reference.  Eigen is not available here; the
+// angle-axis angle of R1^T R2 is computed through the quaternion, as Eigen does.
+namespace {
+struct Pose { float R[3][3]; float t[3]; unsigned votes; };
+
+void quat_from_rot(const float R[3][3], float q[4]) {   // (x, y, z, w), Eigen's Shepperd variant
+    float tr = R[0][0] + R[1][1] + R[2][2];
+    if (tr > 0.f) {
+        float s = std::sqrt(tr + 1.0f);
+        q[3] = 0.5f * s; s = 0.5f / s;
+        q[0] = (R[2][1] - R[1][2]) * s; q[1] = (R[0][2] - R[2][0]) * s; q[2] = (R[1][0] - R[0][1]) * s;
+    } else {
+        int i = 0;
+        if (R[1][1] > R[0][0]) i = 1;
+        if (R[2][2] > R[i][i]) i = 2;
+        int j = (i + 1) % 3, k = (j + 1) % 3;
+        float s = std::sqrt(R[i][i] - R[j][j] - R[k][k] + 1.0f);
+        q[i] = 0.5f * s; s = 0.5f / s;
+        q[3] = (R[k][j] - R[j][k]) * s; q[j] = (R[j][i] + R[i][j]) * s; q[k] = (R[k][i] + R[i][k]) * s;
+    }
+}
+float rotation_angle_between(const Pose &a, const Pose &b) {
+    float D[3][3];
+    for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) D[i][j] = a.R[0][i] * b.R[0][j] + a.R[1][i] * b.R[1][j] + a.R[2][i] * b.R[2][j];
+    float q[4];
+    quat_from_rot(D, q);
+    float n = std::sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2]);
+    return std::fabs(2.0f * std::atan2(n, std::fabs(q[3])));
+}
+bool within_bounds(const Pose &a, const Pose &b, float tt, float rt) {
+    float dx = a.t[0] - b.t[0], dy = a.t[1] - b.t[1], dz = a.t[2] - b.t[2];
+    return std::sqrt(dx * dx + dy * dy + dz * dz) < tt && rotation_angle_between(a, b) < rt;
+}
+// returns the best cluster's averaged pose (row-major 4x4)
+bool cluster_poses_cpu(std::vector<Pose> &poses, float tt, float rt, float out[16]) {
+    std::stable_sort(poses.begin(), poses.end(), [](const Pose &a, const Pose &b) { return a.votes > b.votes; });
+    std::vector<std::vector<int>> clusters;
+    std::vector<std::pair<size_t, unsigned>> cv;
+    for (size_t i = 0; i < poses.size(); i++) {
+        bool found = false;
+        for (size_t c = 0; c < clusters.size(); c++)
+            if (within_bounds(poses[i], poses[clusters[c][0]], tt, rt)) {
+                clusters[c].push_back((int)i); cv[c].second += poses[i].votes; found = true; break;
+            }
+        if (!found) { clusters.push_back({(int)i}); cv.push_back({clusters.size() - 1, poses[i].votes}); }
+    }
+    if (clusters.empty()) return false;
+    std::stable_sort(cv.begin(), cv.end(), [](const std::pair<size_t, unsigned> &a, const std::pair<size_t, unsigned> &b) { return a.second > b.second; });
+    const std::vector<int> &best = clusters[cv[0].first];
+    float ta[3] = {0, 0, 0}, qa[4] = {0, 0, 0, 0};
+    for (int i : best) {
+        float q[4];
+        quat_from_rot(poses[i].R, q);
+        for (int k = 0; k < 3; k++) ta[k] += poses[i].t[k];
+        for (int k = 0; k < 4; k++) qa[k] += q[k];
+    }
+    float inv = 1.0f / (float)best.size();
+    for (int k = 0; k < 3; k++) ta[k] *= inv;
+    float qn = 0;
+    for (int k = 0; k < 4; k++) { qa[k] *= inv; qn += qa[k] * qa[k]; }
+    qn = std::sqrt(qn);
+    float x = qa[0] / qn, y = qa[1] / qn, z = qa[2] / qn, w = qa[3] / qn;
+    float Rm[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+                      {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+                      {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}};
+    for (int i = 0; i < 3; i++) { for (int j = 0; j < 3; j++) out[i * 4 + j] = Rm[i][j]; out[i * 4 + 3] = ta[i]; }
+    out[12] = out[13] = out[14] = 0; out[15] = 1;
+    return true;
+}
+}  // namespace
+
+extern "C" int ppf_lookup_cluster_cpu(const ppf_model_t *m, ppf_lookup_t *lk, float *pose_out) {
+    PPF_CHECK_ARG(m && lk && pose_out, "cluster_cpu: NULL argument");
+    size_t K = lk->res.K;
+    std::memset(pose_out, 0, 64);
+    if (!K) return PPF_OK;
+    std::vector<float> T(K * 16);
+    std::vector<uint32_t> cnt(K);
+    PPF_CUDA_TRY(cudaMemcpy(T.data(), lk->res.transformations, K * 64, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(cudaMemcpy(cnt.data(), lk->res.counts, K * 4, cudaMemcpyDeviceToHost));
+    std::vector<Pose> poses(K);
+    for (size_t i = 0; i < K; i++) {
+        for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) poses[i].R[r][c] = T[i * 16 + r * 4 + c]; poses[i].t[r] = T[i * 16 + r * 4 + 3]; }
+        poses[i].votes = cnt[i];
+    }
+    cluster_poses_cpu(poses, m->table.d_dist, d_angle0(), pose_out);
+    return PPF_OK;
+}
+
+// ---- the drop-in boundary: ppf_registration (ppf.h:9-15, ppf.cu:29-106) -------------------
+extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes, const ppf_cloud_t *model_clouds,
+                                int num_models, const float *model_d_dists, unsigned ref_point_downsample_factor,
+                                float vote_count_threshold, int cpu_clustering, int use_l1_norm,
+                                int use_averaged_clusters, int device, const float *model_weights,
+                                float *poses_out, int *status_out) {
+    (void)model_weights;                                           // ignored by the reference too (ppf.cu:35)
+    PPF_CHECK_ARG(scene_clouds && model_clouds && model_d_dists && poses_out && num_scenes >= 0 && num_models >= 0,
+                  "registration: NULL argument");
+    int ndev = 0;
+    PPF_CUDA_TRY(cudaGetDeviceCount(&ndev));
+    if (ndev < 1) { set_last_error("registration: no CUDA device"); return PPF_ERR_CUDA; }
+    PPF_CUDA_TRY(cudaSetDevice(std::min(ndev - 1, std::max(device, 0))));   // ppf.cu:45
+    std::memset(poses_out, 0, (size_t)num_scenes * num_models * 64);
+    // The reference rebuilds Scene and Model for every (scene, model) pair (ppf.cu:63-70). The model
+    // table depends only on (model, d_dist), so it is built once per model and reused across scenes;
+    // the uploaded scene cloud does not depend on d_dist at all and is reused across models.
+    std::vector<ppf_model_t *> models(num_models, nullptr);
+    int rc = PPF_OK;
+    for (int j = 0; j < num_models && !rc; j++) {
+        const ppf_cloud_t &c = model_clouds[j];
+        rc = ppf_model_create(c.xyz, c.xyz_stride, c.nrm, c.nrm_stride, c.n, PPF_MEM_HOST, model_d_dists[j],
+                              vote_count_threshold, use_l1_norm, use_averaged_clusters, &models[j]);
+    }
+    ppf_lookup_t *lk = nullptr;
+    if (!rc) rc = ppf_lookup_create(&lk);
+    for (int i = 0; i < num_scenes && !rc; i++) {
+        const ppf_cloud_t &c = scene_clouds[i];
+        ppf_scene_t *scene = nullptr;
+        rc = ppf_scene_create(c.xyz, c.xyz_stride, c.nrm, c.nrm_stride, c.n, PPF_MEM_HOST, &scene);
+        for (int j = 0; j < num_models && !rc; j++) {
+            float *pose = poses_out + ((size_t)i * num_models + j) * 16;
+            int st = ppf_model_lookup(models[j], scene, ref_point_downsample_factor, lk);
+            if (st == PPF_OK) {
+                if (cpu_clustering) st = ppf_lookup_cluster_cpu(models[j], lk, pose);      // ppf.cu:75-77
+                else st = ppf_lookup_get(lk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pose);
+            }
+            if (status_out) status_out[(size_t)i * num_models + j] = st;
+            if (st != PPF_OK && st != PPF_ERR_NO_VOTES) rc = st;
+        }
+        ppf_scene_destroy(scene);
+    }
+    ppf_lookup_destroy(lk);
+    for (auto *m : models) ppf_model_destroy(m);
+    return rc;
+}

@@ -1,0 +1,104 @@
+// ppf_internal.cuh -- device-resident objects shared by the translation units.
+//
+// HBM layout (all arrays are plain device allocations owned by the handle):
+//
+//   Cloud      pos[N]   float4 (x, y, z, 0)            -- 16 B vector loads
+//              nrm[N]   float4 (nx, ny, nz, |n|)        -- |n| = sqrt.approx(n.n), hoisted out of the pair loop
+//              fy[N], fz[N] float4                      -- rows y and z of the local frame T_g of each point
+//                                                          (trans_model_scene, kernel.cu:310-327), computed once
+//                                                          per point instead of once per vote
+//   ModelTable hashkeys[U] counts[U] first[U] map[N*N]  -- the reference's ParallelHashArray contents
+//                                                          (parallel_hash_array.hpp:36-46) as u32
+//              entries[N*N] u32                         -- voting payload in bucket order:
+//                                                          [m_r - chunk_base : 12 | theta_u : 19 | slow : 1]
+//              ranges[n_chunks][U] uint2                -- (start, len) of the part of bucket b whose model
+//                                                          reference points fall in chunk c (buckets ascend in
+//                                                          m_r, so every chunk is one contiguous slice)
+//              cell2bucket[K_d * 17^3] u32              -- quantised feature cell -> bucket index or kNoBucket;
+//                                                          replaces hash + binary search on the scene side
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "ppf_math.cuh"
+
+namespace ppf {
+
+// Shared-memory vote accumulator geometry: 31 alpha bins x chunk_rows u32 counters.
+constexpr int kMaxChunkRows = 1536;          // 31 * 1536 * 4 B = 190,464 B
+constexpr int kHitQueue     = 2048;          // 16 B each
+constexpr int kModelLocBits = 12;
+
+struct Cloud {
+    int n = 0;
+    float4 *pos = nullptr, *nrm = nullptr, *fy = nullptr, *fz = nullptr;
+};
+
+struct ModelTable {
+    Cloud cloud;
+    float d_dist = 0.f, inv_d_dist = 0.f;
+    uint32_t U = 0;                           // unique keys
+    uint32_t *hashkeys = nullptr, *counts = nullptr, *first = nullptr, *map = nullptr;
+    uint32_t *entries = nullptr;
+    int n_chunks = 0, chunk_rows = 0;
+    uint2 *ranges = nullptr;
+    int K_d = 0;
+    uint32_t *cell2bucket = nullptr;
+    float *weights = nullptr;                 // modelPointVoteWeights, all 1.0 (model.cu:67)
+    // options carried by the reference's Model object (model.h:43-46)
+    float vote_count_threshold = 0.4f;
+    int use_l1_norm = 0, use_averaged_clusters = 0;
+};
+
+struct VoteResult {                           // device buffers of one ppf_lookup
+    // candidates emitted by the vote kernel (superset of the survivors)
+    unsigned long long *cand_codes = nullptr;
+    uint32_t *cand_counts = nullptr;
+    size_t cand_cap = 0;
+    // device scalars: [0]=cand_n [1]=global max count [2]=non-zero cells (num_unique_votes)
+    // [3]=overflow flag ; votes_total (u64) separately
+    uint32_t *scalars = nullptr;
+    unsigned long long *votes_total = nullptr;
+    // survivors, ordered (count desc, code asc) -- model.cu:155-170
+    size_t K = 0;
+    unsigned long long *codes = nullptr;
+    uint32_t *counts = nullptr;
+    float *transformations = nullptr;         // K*16
+    float *weighted = nullptr;                // K
+    float3 *trans = nullptr;                  // K
+    float4 *rots = nullptr;                   // K
+    float *scores = nullptr;                  // K  (vote_counts_out)
+    uint32_t max_idx = 0;
+    size_t cap_K = 0;
+};
+
+// error plumbing (never exit(): SURVEY 8b "Errors")
+void set_last_error(const std::string &msg);
+#define PPF_CUDA_TRY(expr)                                                                 \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            ::ppf::set_last_error(std::string(#expr) + ": " + cudaGetErrorString(_e));     \
+            return PPF_ERR_CUDA;                                                           \
+        }                                                                                  \
+    } while (0)
+
+// ---- entry points of the translation units -------------------------------------------
+int  cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, Cloud &c);
+void cloud_free(Cloud &c);
+int  features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int ob, int oe,
+                   float *ppfs_host, uint32_t *keys_host);
+int  model_build(ModelTable &m);
+void model_free(ModelTable &m);
+int  model_table_get(const ModelTable &m, uint32_t *hashkeys, size_t *counts, size_t *first, size_t *map);
+int  vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_rank, int shard_count,
+              int emit_all, VoteResult &r, unsigned long long *pairs_out, int *launches);
+int  vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteResult &r);
+int  order_survivors(VoteResult &r, size_t K, unsigned long long *codes_in, uint32_t *counts_in);
+int  vote_reserve_K(VoteResult &r, size_t K);
+void vote_result_free(VoteResult &r);
+int  poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r);
+int  cluster_run(const ModelTable &m, VoteResult &r);
+
+}  // namespace ppf

@@ -1,0 +1,377 @@
+// ppf_model.cu -- cloud upload, per-point local frames, and the model hash-table
+// build (model_description).  Replaces Scene::initPPFs (scene.cu:64-99),
+// Model::Model (model.cu:43-82) and ParallelHashArray's constructor
+// (parallel_hash_array.hpp:55-77) + histogram (util.hpp:30-52).
+//
+// Differences from the reference, none of which change results:
+//  * no N*N float4 feature matrix: one fused kernel goes point pair -> feature bins
+//    -> FNV key (+ the vote payload theta_u), 8 B written per pair instead of 20 B;
+//  * pair indices are u32 (N <= 46340, the reference's own int limit) so the radix
+//    sort moves 8 B per pair and pass instead of 12 B;
+//  * the vote payload (chunk-local m_r, alpha_m as a 19-bit binary angle) is
+//    gathered into bucket order once, so voting streams 4 B per vote.
+#include <cub/cub.cuh>
+#include <vector>
+
+#include "../../include/ppf_b200.h"
+#include "ppf_internal.cuh"
+
+namespace ppf {
+
+// ---------------------------------------------------------------------------------
+// Cloud
+// ---------------------------------------------------------------------------------
+__global__ void pack_cloud_kernel(const float *__restrict__ xyz, int xs, const float *__restrict__ nrm,
+                                  int ns, int n, float4 *pos, float4 *nrmo, float4 *fy, float4 *fz) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float px = xyz[(size_t)i * xs], py = xyz[(size_t)i * xs + 1], pz = xyz[(size_t)i * xs + 2];
+    float nx = nrm[(size_t)i * ns], ny = nrm[(size_t)i * ns + 1], nz = nrm[(size_t)i * ns + 2];
+    pos[i] = make_float4(px, py, pz, 0.f);
+    nrmo[i] = make_float4(nx, ny, nz, norm3(nx, ny, nz));
+    FrameYZ f = frame_yz(px, py, pz, nx, ny, nz);
+    fy[i] = make_float4(f.y[0], f.y[1], f.y[2], f.y[3]);
+    fz[i] = make_float4(f.z[0], f.z[1], f.z[2], f.z[3]);
+}
+
+void cloud_free(Cloud &c) {
+    cudaFree(c.pos); cudaFree(c.nrm); cudaFree(c.fy); cudaFree(c.fz);
+    c = Cloud();
+}
+
+int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, Cloud &c) {
+    if (!xyz || !nrm || n < 0 || xs < 3 || ns < 3) {
+        set_last_error("cloud: null pointer, negative size or stride < 3");
+        return PPF_ERR_INVALID;
+    }
+    c.n = n;
+    size_t nn = n > 0 ? (size_t)n : 1;
+    PPF_CUDA_TRY(cudaMalloc(&c.pos, nn * sizeof(float4)));
+    PPF_CUDA_TRY(cudaMalloc(&c.nrm, nn * sizeof(float4)));
+    PPF_CUDA_TRY(cudaMalloc(&c.fy, nn * sizeof(float4)));
+    PPF_CUDA_TRY(cudaMalloc(&c.fz, nn * sizeof(float4)));
+    if (n == 0) return PPF_OK;
+    const float *dx = xyz, *dn = nrm;
+    float *tmpx = nullptr, *tmpn = nullptr;
+    if (mem == PPF_MEM_HOST) {
+        size_t bx = ((size_t)(n - 1) * xs + 3) * sizeof(float), bn = ((size_t)(n - 1) * ns + 3) * sizeof(float);
+        PPF_CUDA_TRY(cudaMalloc(&tmpx, bx));
+        PPF_CUDA_TRY(cudaMalloc(&tmpn, bn));
+        PPF_CUDA_TRY(cudaMemcpyAsync(tmpx, xyz, bx, cudaMemcpyHostToDevice, 0));
+        PPF_CUDA_TRY(cudaMemcpyAsync(tmpn, nrm, bn, cudaMemcpyHostToDevice, 0));
+        dx = tmpx; dn = tmpn;
+    }
+    pack_cloud_kernel<<<(n + 255) / 256, 256>>>(dx, xs, dn, ns, n, c.pos, c.nrm, c.fy, c.fz);
+    PPF_CUDA_TRY(cudaGetLastError());
+    if (tmpx) { PPF_CUDA_TRY(cudaStreamSynchronize(0)); cudaFree(tmpx); cudaFree(tmpn); }
+    return PPF_OK;
+}
+
+__device__ __forceinline__ PointN load_point(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, int i) {
+    float4 p = __ldg(pos + i), q = __ldg(nrm + i);
+    PointN r;
+    r.x = p.x; r.y = p.y; r.z = p.z; r.nx = q.x; r.ny = q.y; r.nz = q.z; r.nn = q.w;
+    return r;
+}
+
+// ---------------------------------------------------------------------------------
+// Debug / parity view: quantised features + keys of a tile (ppf_kernel + ppf_hash_kernel)
+// ---------------------------------------------------------------------------------
+__global__ void features_tile_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, int n,
+                                     float d_dist, float inv_d, unsigned df, int rb, int re, int ob, int oe,
+                                     float4 *ppfs, uint32_t *keys) {
+    size_t w = (size_t)(oe - ob), total = (size_t)(re - rb) * w;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        int r = rb + (int)(t / w), o = ob + (int)(t % w);
+        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
+        uint32_t key = 0;
+        if (n <= 1) {
+            // ppf_kernel / ppf_hash_kernel return early for count <= 1: zero-initialised memory
+        } else if ((r % df) != 0 || r == o) {
+            out.x = CUDART_NAN_F;                                    // kernel.cu:432-441
+        } else {
+            PointN a = load_point(pos, nrm, r), b = load_point(pos, nrm, o);
+            FeatureBins fb = pair_feature_bins(a, b, d_dist, inv_d);
+            // kd == INT_MAX marks a distance more than 4e6 bins away: no table can hold it, so only
+            // this debug view needs its quantised value; use the reference's own formula there.
+            if (fb.kd < 0) out.x = CUDART_NAN_F;
+            else if (fb.kd == 0x7FFFFFFF) out.x = __fsub_rn(fb.f1, fmodf(fb.f1, d_dist));
+            else out.x = quant_value(fb.kd, d_dist);
+            out.y = __uint_as_float(angle_bits(fb.k1));
+            out.z = __uint_as_float(angle_bits(fb.k2));
+            out.w = __uint_as_float(angle_bits(fb.k3));
+            key = (out.x != out.x) ? 0u
+                                   : fnv1a_4(__float_as_uint(out.x), __float_as_uint(out.y),
+                                             __float_as_uint(out.z), __float_as_uint(out.w));
+        }
+        if (ppfs) ppfs[t] = out;
+        if (keys) keys[t] = key;
+    }
+}
+
+int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int ob, int oe, float *ppfs_host,
+                  uint32_t *keys_host) {
+    if (rb < 0 || ob < 0 || re > c.n || oe > c.n || rb > re || ob > oe || df == 0 || !(d_dist > 0.f)) {
+        set_last_error("features: bad tile bounds, df == 0 or d_dist <= 0");
+        return PPF_ERR_INVALID;
+    }
+    size_t total = (size_t)(re - rb) * (size_t)(oe - ob);
+    if (total == 0) return PPF_OK;
+    float4 *dp = nullptr; uint32_t *dk = nullptr;
+    if (ppfs_host) PPF_CUDA_TRY(cudaMalloc(&dp, total * sizeof(float4)));
+    if (keys_host) PPF_CUDA_TRY(cudaMalloc(&dk, total * sizeof(uint32_t)));
+    int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
+    features_tile_kernel<<<blocks, 256>>>(c.pos, c.nrm, c.n, d_dist, 1.0f / d_dist, df, rb, re, ob, oe, dp, dk);
+    PPF_CUDA_TRY(cudaGetLastError());
+    if (dp) PPF_CUDA_TRY(cudaMemcpy(ppfs_host, dp, total * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (dk) PPF_CUDA_TRY(cudaMemcpy(keys_host, dk, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    cudaFree(dp); cudaFree(dk);
+    return PPF_OK;
+}
+
+// ---------------------------------------------------------------------------------
+// Model table build
+// ---------------------------------------------------------------------------------
+// One thread per ordered model pair p = m_r*N + m_i (coalesced along m_i):
+//   key[p]   = FNV-1a of the quantised feature (0 for the self pair)   -- ppf_kernel + ppf_hash_kernel
+//   theta[p] = 19-bit binary angle of u = (T_mg m_i).yz, bit 31 = slow  -- alpha_m of Drost et al.
+__global__ void __launch_bounds__(256) model_pairs_kernel(const float4 *__restrict__ pos,
+                                                          const float4 *__restrict__ nrm,
+                                                          const float4 *__restrict__ fy,
+                                                          const float4 *__restrict__ fz, int n, float d_dist,
+                                                          float inv_d, uint32_t *keys, uint32_t *theta,
+                                                          int *max_kd) {
+    size_t total = (size_t)n * n;
+    int local_max = -1;
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        int r = (int)(p / n), i = (int)(p - (size_t)r * n);
+        uint32_t key = 0, th = 0;
+        if (r != i) {
+            PointN a = load_point(pos, nrm, r), b = load_point(pos, nrm, i);
+            FeatureBins fb = pair_feature_bins(a, b, d_dist, inv_d);
+            key = feature_key(fb.kd, fb.k1, fb.k2, fb.k3, d_dist);
+            if (fb.kd >= 0) local_max = max(local_max, fb.kd);
+            float4 y = __ldg(fy + r), z = __ldg(fz + r);
+            FrameYZ f;
+            f.y[0] = y.x; f.y[1] = y.y; f.y[2] = y.z; f.y[3] = y.w;
+            f.z[0] = z.x; f.z[1] = z.y; f.z[2] = z.z; f.z[3] = z.w;
+            float uy, uz;
+            frame_apply_yz(f, b.x, b.y, b.z, uy, uz);
+            th = theta_code(uy, uz);
+        }
+        keys[p] = key;
+        theta[p] = th;
+    }
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 16));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 8));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 4));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 2));
+    local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 1));
+    if ((threadIdx.x & 31) == 0 && local_max >= 0) atomicMax(max_kd, local_max);
+}
+
+__global__ void iota_kernel(uint32_t *v, size_t n) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        v[i] = (uint32_t)i;
+}
+
+// entries[q] = [m_r - chunk_base : 12 | theta : 19 | slow : 1] for sorted position q
+__global__ void gather_entries_kernel(const uint32_t *__restrict__ map, const uint32_t *__restrict__ theta,
+                                      size_t total, int n, int chunk_rows, uint32_t *entries) {
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        uint32_t p = map[q];
+        uint32_t th = __ldg(theta + p);
+        uint32_t r = p / (uint32_t)n;
+        uint32_t loc = r % (uint32_t)chunk_rows;
+        entries[q] = (loc << 20) | ((th & kThetaMask) << 1) | (th >> 31);
+    }
+}
+
+// ranges[c][b] = slice of bucket b with m_r in [c*chunk_rows, (c+1)*chunk_rows)
+__global__ void chunk_ranges_kernel(const uint32_t *__restrict__ map, const uint32_t *__restrict__ first,
+                                    const uint32_t *__restrict__ counts, uint32_t U, int n, int chunk_rows,
+                                    int n_chunks, uint2 *ranges) {
+    size_t total = (size_t)U * n_chunks;
+    for (size_t t = blockIdx.x * (size_t)blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
+        uint32_t b = (uint32_t)(t % U);
+        int c = (int)(t / U);
+        uint32_t lo0 = first[b], hi0 = lo0 + counts[b];
+        uint32_t bound[2];
+#pragma unroll
+        for (int s = 0; s < 2; s++) {
+            unsigned long long want = (unsigned long long)(c + s) * chunk_rows * (unsigned long long)n;
+            uint32_t lo = lo0, hi = hi0;
+            while (lo < hi) {
+                uint32_t mid = lo + ((hi - lo) >> 1);
+                if ((unsigned long long)map[mid] < want) lo = mid + 1; else hi = mid;
+            }
+            bound[s] = lo;
+        }
+        ranges[(size_t)c * U + b] = make_uint2(bound[0], bound[1] - bound[0]);
+    }
+}
+
+// cell -> bucket: hash the cell's quantised feature the way ppf_hash_kernel would and
+// binary-search it in the unique keys (ParallelHashArray::GetIndices + the hit test of
+// ppf_vote_count_kernel, kernel.cu:489-497).  Key 0 is the reference's "invalid" marker.
+__global__ void cell_table_kernel(const uint32_t *__restrict__ hashkeys, uint32_t U, int K_d, float d_dist,
+                                  uint32_t *cell2bucket) {
+    int total = K_d * kCellsPerDist;
+    for (int cidx = blockIdx.x * blockDim.x + threadIdx.x; cidx < total; cidx += gridDim.x * blockDim.x) {
+        int k3 = cidx % kAngleCells, t = cidx / kAngleCells;
+        int k2 = t % kAngleCells; t /= kAngleCells;
+        int k1 = t % kAngleCells; int kd = t / kAngleCells;
+        uint32_t key = feature_key(kd, k1, k2, k3, d_dist);
+        uint32_t res = kNoBucket;
+        if (key != 0u) {
+            uint32_t lo = 0, hi = U;
+            while (lo < hi) {
+                uint32_t mid = lo + ((hi - lo) >> 1);
+                if (hashkeys[mid] < key) lo = mid + 1; else hi = mid;
+            }
+            if (lo < U && hashkeys[lo] == key) res = lo;
+        }
+        cell2bucket[cidx] = res;
+    }
+}
+
+__global__ void fill_kernel(float *v, int n, float x) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) v[i] = x;
+}
+
+void model_free(ModelTable &m) {
+    cloud_free(m.cloud);
+    cudaFree(m.hashkeys); cudaFree(m.counts); cudaFree(m.first); cudaFree(m.map);
+    cudaFree(m.entries); cudaFree(m.ranges); cudaFree(m.cell2bucket); cudaFree(m.weights);
+    m = ModelTable();
+}
+
+int model_build(ModelTable &m) {
+    const int n = m.cloud.n;
+    if (n > PPF_MAX_MODEL_POINTS) {
+        set_last_error("model: more than 46340 points (N*N pair indices must stay below 2^31, as in the reference)");
+        return PPF_ERR_UNSUPPORTED;
+    }
+    if (!(m.d_dist > 0.f)) { set_last_error("model: d_dist must be > 0"); return PPF_ERR_INVALID; }
+    m.inv_d_dist = 1.0f / m.d_dist;
+    m.n_chunks = std::max(1, (n + kMaxChunkRows - 1) / kMaxChunkRows);
+    m.chunk_rows = std::max(32, (((n + m.n_chunks - 1) / m.n_chunks) + 31) / 32 * 32);
+    PPF_CUDA_TRY(cudaMalloc(&m.weights, std::max(1, n) * sizeof(float)));
+    if (n > 0) fill_kernel<<<(n + 255) / 256, 256>>>(m.weights, n, 1.0f);
+    // Every reference kernel returns early when count <= 1 (kernel.cu:406,461): a model with
+    // fewer than two points has an all-zero key array, i.e. one bucket (key 0) that can never match.
+    size_t total = (size_t)n * n;
+    if (n <= 1) {
+        m.U = (uint32_t)total;              // n==1: one key (0); n==0: none
+        m.K_d = 0;
+        PPF_CUDA_TRY(cudaMalloc(&m.hashkeys, 4)); PPF_CUDA_TRY(cudaMalloc(&m.counts, 4));
+        PPF_CUDA_TRY(cudaMalloc(&m.first, 4)); PPF_CUDA_TRY(cudaMalloc(&m.map, 4));
+        PPF_CUDA_TRY(cudaMalloc(&m.entries, 4)); PPF_CUDA_TRY(cudaMalloc(&m.ranges, 8));
+        PPF_CUDA_TRY(cudaMalloc(&m.cell2bucket, 4));
+        uint32_t z = 0, one = 1;
+        cudaMemcpy(m.hashkeys, &z, 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(m.counts, &one, 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(m.first, &z, 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(m.map, &z, 4, cudaMemcpyHostToDevice);
+        return PPF_OK;
+    }
+
+    uint32_t *keys = nullptr, *keys_sorted = nullptr, *theta = nullptr, *iota = nullptr, *d_U = nullptr;
+    int *d_maxkd = nullptr;
+    PPF_CUDA_TRY(cudaMalloc(&keys, total * 4));
+    PPF_CUDA_TRY(cudaMalloc(&theta, total * 4));
+    PPF_CUDA_TRY(cudaMalloc(&d_maxkd, 4));
+    PPF_CUDA_TRY(cudaMemset(d_maxkd, 0xFF, 4));
+    int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
+    model_pairs_kernel<<<grid, 256>>>(m.cloud.pos, m.cloud.nrm, m.cloud.fy, m.cloud.fz, n, m.d_dist,
+                                      m.inv_d_dist, keys, theta, d_maxkd);
+    PPF_CUDA_TRY(cudaGetLastError());
+
+    // sort (key, pair index): LSD radix sort, stable, so every bucket ascends in pair index
+    PPF_CUDA_TRY(cudaMalloc(&keys_sorted, total * 4));
+    PPF_CUDA_TRY(cudaMalloc(&iota, total * 4));
+    PPF_CUDA_TRY(cudaMalloc(&m.map, total * 4));
+    iota_kernel<<<grid, 256>>>(iota, total);
+    void *tmp = nullptr; size_t tmp_bytes = 0;
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, iota, m.map, total));
+    PPF_CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, iota, m.map, total));
+    cudaFree(tmp); tmp = nullptr;
+    cudaFree(iota); cudaFree(keys);
+
+    // run-length encode -> unique keys + counts (histogram(), util.hpp:30-52); scan -> first index
+    uint32_t *uk = nullptr, *uc = nullptr;
+    PPF_CUDA_TRY(cudaMalloc(&uk, total * 4));
+    PPF_CUDA_TRY(cudaMalloc(&uc, total * 4));
+    PPF_CUDA_TRY(cudaMalloc(&d_U, 4));
+    tmp_bytes = 0;
+    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, keys_sorted, uk, uc, d_U, total));
+    PPF_CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
+    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, keys_sorted, uk, uc, d_U, total));
+    cudaFree(tmp); tmp = nullptr;
+    int h_maxkd = -1;
+    PPF_CUDA_TRY(cudaMemcpy(&m.U, d_U, 4, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(cudaMemcpy(&h_maxkd, d_maxkd, 4, cudaMemcpyDeviceToHost));
+    cudaFree(d_U); cudaFree(d_maxkd); cudaFree(keys_sorted);
+    if (h_maxkd >= 65536) {
+        cudaFree(uk); cudaFree(uc); cudaFree(theta);
+        set_last_error("model: d_dist is more than 65536x smaller than the model extent");
+        return PPF_ERR_UNSUPPORTED;
+    }
+    m.K_d = h_maxkd + 1;
+    PPF_CUDA_TRY(cudaMalloc(&m.hashkeys, m.U * 4));
+    PPF_CUDA_TRY(cudaMalloc(&m.counts, m.U * 4));
+    PPF_CUDA_TRY(cudaMalloc(&m.first, m.U * 4));
+    PPF_CUDA_TRY(cudaMemcpy(m.hashkeys, uk, m.U * 4, cudaMemcpyDeviceToDevice));
+    PPF_CUDA_TRY(cudaMemcpy(m.counts, uc, m.U * 4, cudaMemcpyDeviceToDevice));
+    cudaFree(uk); cudaFree(uc);
+    tmp_bytes = 0;
+    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, m.counts, m.first, m.U));
+    PPF_CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
+    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, m.counts, m.first, m.U));
+    cudaFree(tmp); tmp = nullptr;
+
+    // vote payload in bucket order, per-chunk bucket slices, cell table
+    PPF_CUDA_TRY(cudaMalloc(&m.entries, total * 4));
+    gather_entries_kernel<<<grid, 256>>>(m.map, theta, total, n, m.chunk_rows, m.entries);
+    PPF_CUDA_TRY(cudaGetLastError());
+    PPF_CUDA_TRY(cudaMalloc(&m.ranges, (size_t)m.U * m.n_chunks * sizeof(uint2)));
+    {
+        size_t t = (size_t)m.U * m.n_chunks;
+        chunk_ranges_kernel<<<(int)std::min<size_t>((t + 255) / 256, 148 * 32), 256>>>(
+            m.map, m.first, m.counts, m.U, n, m.chunk_rows, m.n_chunks, m.ranges);
+    }
+    PPF_CUDA_TRY(cudaGetLastError());
+    size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
+    PPF_CUDA_TRY(cudaMalloc(&m.cell2bucket, ncell * 4));
+    if (m.K_d > 0)
+        cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256>>>(m.hashkeys, m.U, m.K_d,
+                                                                                       m.d_dist, m.cell2bucket);
+    PPF_CUDA_TRY(cudaGetLastError());
+    PPF_CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(theta);
+    return PPF_OK;
+}
+
+int model_table_get(const ModelTable &m, uint32_t *hashkeys, size_t *counts, size_t *first, size_t *map) {
+    size_t total = (size_t)m.cloud.n * m.cloud.n;
+    std::vector<uint32_t> tmp;
+    if (hashkeys && m.U) PPF_CUDA_TRY(cudaMemcpy(hashkeys, m.hashkeys, (size_t)m.U * 4, cudaMemcpyDeviceToHost));
+    auto widen = [&](const uint32_t *dev, size_t cnt, size_t *out) -> int {
+        if (!out || !cnt) return PPF_OK;
+        tmp.resize(cnt);
+        PPF_CUDA_TRY(cudaMemcpy(tmp.data(), dev, cnt * 4, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < cnt; i++) out[i] = tmp[i];
+        return PPF_OK;
+    };
+    int rc;
+    if ((rc = widen(m.counts, m.U, counts))) return rc;
+    if ((rc = widen(m.first, m.U, first))) return rc;
+    if (m.cloud.n >= 2) { if ((rc = widen(m.map, total, map))) return rc; }
+    else if (map && total) map[0] = 0;
+    if (m.cloud.n <= 1 && counts && m.U) counts[0] = total;
+    return PPF_OK;
+}
+
+}  // namespace ppf

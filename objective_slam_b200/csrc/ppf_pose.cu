@@ -1,0 +1,248 @@
+// ppf_pose.cu -- pose from vote, vote weighting and GPU pose clustering.
+// Replaces trans_calc_kernel2 (kernel.cu:605-645) with compute_rot_angles /
+// compute_transforms (kernel.cu:352-401), vote_weight_kernel (kernel.cu:766-782),
+// mat2transquat_kernel (kernel.cu:647-661), trans2idx_kernel (kernel.cu:663-699),
+// the second ParallelHashArray + GetIndices (model.cu:222-226) and
+// rot_clustering_kernel (kernel.cu:702-763), plus thrust::max_element (model.cu:293-295).
+//
+// K (surviving votes) is 10^2..10^5, so these kernels are latency-bound; what matters
+// is that they reproduce the reference's arithmetic and its quirks:
+//   * every kernel is a no-op when K <= 1 (kernel.cu:609,651,667,712,769) -> zero pose;
+//   * the all-zero vote code is skipped (kernel.cu:628-631);
+//   * the pose uses the lower edge of the alpha bin: Rx(alpha_idx*D_ANGLE0 - pi), an FFMA;
+//   * quaternion normalised by sqrt(norm(q)) (kernel.cu:138);
+//   * cells are matched by 32-bit FNV hash of (int)(quant_down(t)/d_dist), the pose's own
+//     cell is excluded (hash forced to 0, kernel.cu:684-689) and hash 0 means "skip".
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/ppf_b200.h"
+#include "ppf_internal.cuh"
+
+namespace ppf {
+
+// invht (kernel.cu:254-299)
+__device__ __forceinline__ void mat4_invht(const Mat4 &T, Mat4 &Ti) {
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) Ti.m[i][j] = T.m[j][i];
+    float tx = T.m[0][3], ty = T.m[1][3], tz = T.m[2][3];
+#pragma unroll
+    // -R' t.  nvcc rewrites the negated dot product as ((-r1*ty) - r0*tx) - r2*tz and ptxas fuses it
+    // into fma(-r2, tz, fma(-r1, ty, -(r0*tx))) (reference SASS of trans_calc_kernel2): the plain
+    // product is the x term here, unlike every other dot product of the reference.
+    for (int i = 0; i < 3; i++)
+        Ti.m[i][3] = __fmaf_rn(-Ti.m[i][2], tz, __fmaf_rn(-Ti.m[i][1], ty, -__fmul_rn(Ti.m[i][0], tx)));
+    Ti.m[3][0] = 0; Ti.m[3][1] = 0; Ti.m[3][2] = 0; Ti.m[3][3] = 1;
+}
+
+__global__ void pose_kernel(const unsigned long long *__restrict__ votes, const float4 *mpos, const float4 *mnrm,
+                            const float4 *spos, const float4 *snrm, float *transforms, int count) {
+    if (count <= 1) return;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        unsigned long long v = votes[idx];
+        uint32_t s = (uint32_t)(v >> 32), mac = (uint32_t)v, m = mac >> 6, a = mac & 63u;
+        if (s == 0 && m == 0 && a == 0) continue;
+        float4 mn = mnrm[m], sn = snrm[s], mp = mpos[m], sp = spos[s];
+        float m_roty, m_rotz, s_roty, s_rotz;
+        frame_angles(mn.x, mn.y, mn.z, m_roty, m_rotz);
+        frame_angles(sn.x, sn.y, sn.z, s_roty, s_rotz);
+        Mat4 Tmg, Tsg, Rx, Tinv, T2, T;
+        frame_from_angles(mp.x, mp.y, mp.z, m_roty, m_rotz, Tmg);
+        frame_from_angles(sp.x, sp.y, sp.z, s_roty, s_rotz, Tsg);
+        mat4_rotx(__fmaf_rn((float)a, d_angle0(), -CUDART_PI_F), Rx);
+        mat4_invht(Tsg, Tinv);
+        mat4_mul(Tinv, Rx, T2);
+        mat4_mul(T2, Tmg, T);
+        float *out = transforms + (size_t)idx * 16;
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+#pragma unroll
+            for (int j = 0; j < 4; j++) out[i * 4 + j] = T.m[i][j];
+    }
+}
+
+__global__ void weight_kernel(const unsigned long long *votes, const uint32_t *counts, const float *weights,
+                              float *weighted, int count) {
+    if (count <= 1) return;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        uint32_t m = ((uint32_t)votes[idx]) >> 6;
+        weighted[idx] = __fmul_rn(weights[m], (float)counts[idx]);
+    }
+}
+
+// mat2transquat_kernel + hrotmat2quat (kernel.cu:128-144)
+__global__ void transquat_kernel(const float *T, float3 *trans, float4 *rots, int count) {
+    if (count <= 1) return;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        const float *M = T + (size_t)idx * 16;
+        trans[idx] = make_float3(M[3], M[7], M[11]);
+        float T00 = M[0], T11 = M[5], T22 = M[10];
+        float t = __fadd_rn(__fadd_rn(T00, T11), T22);
+        float4 q;
+        q.x = __fmul_rn(0.5f, sqrt_approx_ftz(__fadd_rn(1.0f, t)));
+        q.y = copysignf(__fmul_rn(0.5f, sqrt_approx_ftz(__fsub_rn(__fsub_rn(__fadd_rn(1.0f, T00), T11), T22))),
+                        __fsub_rn(M[9], M[6]));
+        q.z = copysignf(__fmul_rn(0.5f, sqrt_approx_ftz(__fsub_rn(__fadd_rn(__fsub_rn(1.0f, T00), T11), T22))),
+                        __fsub_rn(M[2], M[8]));
+        q.w = copysignf(__fmul_rn(0.5f, sqrt_approx_ftz(__fadd_rn(__fsub_rn(__fsub_rn(1.0f, T00), T11), T22))),
+                        __fsub_rn(M[4], M[1]));
+        float n = sqrt_approx_ftz(sqrt_approx_ftz(dot4(q.x, q.y, q.z, q.w, q.x, q.y, q.z, q.w)));
+        q.x = div_full_ftz(q.x, n); q.y = div_full_ftz(q.y, n);
+        q.z = div_full_ftz(q.z, n); q.w = div_full_ftz(q.w, n);
+        rots[idx] = q;
+    }
+}
+
+__device__ __forceinline__ int trans_cell(float x, float d) {
+    float disc = __fsub_rn(x, fmodf(x, d));                 // quant_downf, kernel.cu:90-92 (x may be negative)
+    return __float2int_rz(div_full_ftz(disc, d));           // (int)(disc / d_dist), kernel.cu:676-678
+}
+
+// trans2idx_kernel (kernel.cu:663-699)
+__global__ void cellhash_kernel(const float3 *trans, uint32_t *cell_hash, uint32_t *adj_hash, int count, float d) {
+    if (count <= 1) return;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        float3 t = trans[idx];
+        int cx = trans_cell(t.x, d), cy = trans_cell(t.y, d), cz = trans_cell(t.z, d);
+        cell_hash[idx] = fnv1a_3((uint32_t)cx, (uint32_t)cy, (uint32_t)cz);
+        int c = 0;
+        for (int i = -1; i < 2; i++)
+            for (int j = -1; j < 2; j++)
+                for (int k = -1; k < 2; k++, c++) {
+                    uint32_t h = 0;
+                    if (!(i == 0 && j == 0 && k == 0))
+                        h = fnv1a_3((uint32_t)(cx + i), (uint32_t)(cy + j), (uint32_t)(cz + k));
+                    adj_hash[27 * (size_t)idx + c] = h;
+                }
+    }
+}
+
+// rot_clustering_kernel (kernel.cu:702-763). sorted_hash/sorted_idx: poses ordered by
+// (cell hash, pose index) -- the ParallelHashArray of model.cu:222-223.
+__global__ void cluster_kernel(const float3 *trans_in, const float4 *quats, const float *weights,
+                               const uint32_t *adj_hash, const uint32_t *sorted_hash, const uint32_t *sorted_idx,
+                               float *scores, float3 *trans_out, int count, float trans_thresh, int use_l1_norm,
+                               int use_averaged_clusters) {
+    if (count <= 1) return;
+    const float rot_thresh = 2 * d_angle0();                                  // ROT_THRESH, kernel.h:17
+    const float rot_thresh_sq = rot_thresh * rot_thresh;
+    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
+        float3 tt = trans_in[idx];
+        float4 q = quats[idx];
+        float score = 1;
+        float3 to = tt;
+        for (int ab = 0; ab < 27; ab++) {
+            uint32_t h = adj_hash[27 * (size_t)idx + ab];
+            if (h == 0) continue;
+            int lo = 0, hi = count;                                           // lower_bound over the cell hashes
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                if (sorted_hash[mid] < h) lo = mid + 1; else hi = mid;
+            }
+            for (int p = lo; p < count && sorted_hash[p] == h; p++) {
+                uint32_t j = sorted_idx[p];
+                float w = weights[j];
+                float4 qj = quats[j];
+                float qd = fabsf(__fmul_rn(8.0f, __fsub_rn(1.0f, dot4(q.x, q.y, q.z, q.w, qj.x, qj.y, qj.z, qj.w))));
+                if (qd < rot_thresh_sq) {
+                    float3 tj = trans_in[j];
+                    if (!use_l1_norm) {
+                        float nd = norm3(__fsub_rn(tt.x, tj.x), __fsub_rn(tt.y, tj.y), __fsub_rn(tt.z, tj.z));
+                        if (!(nd < trans_thresh)) continue;
+                    }
+                    if (use_averaged_clusters) {                              // kernel.cu:747-752
+                        to.x = __fmul_rn(score, to.x); to.y = __fmul_rn(score, to.y); to.z = __fmul_rn(score, to.z);
+                        to.x = __fadd_rn(to.x, __fmul_rn(w, tj.x));
+                        to.y = __fadd_rn(to.y, __fmul_rn(w, tj.y));
+                        to.z = __fadd_rn(to.z, __fmul_rn(w, tj.z));
+                        float inv = div_full_ftz(1.0f, __fadd_rn(score, w));
+                        to.x = __fmul_rn(inv, to.x); to.y = __fmul_rn(inv, to.y); to.z = __fmul_rn(inv, to.z);
+                    }
+                    score = __fadd_rn(score, w);
+                }
+            }
+        }
+        scores[idx] = score;
+        trans_out[idx] = to;
+    }
+}
+
+// first index of the maximum (thrust::max_element semantics)
+__global__ void argmax_kernel(const float *scores, int count, uint32_t *out) {
+    __shared__ float sv[1024];
+    __shared__ int si[1024];
+    float best = -CUDART_INF_F; int bi = 0x7FFFFFFF;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) {
+        float s = scores[i];
+        if (s > best || (s == best && i < bi)) { best = s; bi = i; }
+    }
+    sv[threadIdx.x] = best; si[threadIdx.x] = bi;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o; o >>= 1) {
+        if (threadIdx.x < o) {
+            float s = sv[threadIdx.x + o]; int i = si[threadIdx.x + o];
+            if (s > sv[threadIdx.x] || (s == sv[threadIdx.x] && i < si[threadIdx.x])) { sv[threadIdx.x] = s; si[threadIdx.x] = i; }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = (count > 0 && si[0] != 0x7FFFFFFF) ? (uint32_t)si[0] : 0u;
+}
+
+static int blocks_for(size_t count) { return (int)std::min<size_t>(std::max<size_t>((count + 255) / 256, 1), 1024); }
+
+int poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r) {
+    const int K = (int)r.K;
+    if (K == 0) return PPF_OK;
+    PPF_CUDA_TRY(cudaMemsetAsync(r.transformations, 0, (size_t)K * 64, 0));
+    PPF_CUDA_TRY(cudaMemsetAsync(r.weighted, 0, (size_t)K * 4, 0));
+    pose_kernel<<<blocks_for(K), 256>>>(r.codes, m.cloud.pos, m.cloud.nrm, scene.pos, scene.nrm, r.transformations, K);
+    weight_kernel<<<blocks_for(K), 256>>>(r.codes, r.counts, m.weights, r.weighted, K);
+    PPF_CUDA_TRY(cudaGetLastError());
+    return PPF_OK;
+}
+
+int cluster_run(const ModelTable &m, VoteResult &r) {
+    const int K = (int)r.K;
+    r.max_idx = 0;
+    if (K == 0) return PPF_OK;
+    PPF_CUDA_TRY(cudaMemsetAsync(r.trans, 0, (size_t)K * sizeof(float3), 0));
+    PPF_CUDA_TRY(cudaMemsetAsync(r.rots, 0, (size_t)K * sizeof(float4), 0));
+    PPF_CUDA_TRY(cudaMemsetAsync(r.scores, 0, (size_t)K * 4, 0));
+    if (K <= 1) return PPF_OK;
+    transquat_kernel<<<blocks_for(K), 256>>>(r.transformations, r.trans, r.rots, K);
+    uint32_t *cell = nullptr, *adj = nullptr, *iota = nullptr, *shash = nullptr, *sidx = nullptr, *d_arg = nullptr;
+    float3 *tin = nullptr;
+    PPF_CUDA_TRY(cudaMalloc(&cell, (size_t)K * 4));
+    PPF_CUDA_TRY(cudaMalloc(&adj, (size_t)K * 27 * 4));
+    PPF_CUDA_TRY(cudaMalloc(&iota, (size_t)K * 4));
+    PPF_CUDA_TRY(cudaMalloc(&shash, (size_t)K * 4));
+    PPF_CUDA_TRY(cudaMalloc(&sidx, (size_t)K * 4));
+    PPF_CUDA_TRY(cudaMalloc(&tin, (size_t)K * sizeof(float3)));
+    PPF_CUDA_TRY(cudaMalloc(&d_arg, 4));
+    cellhash_kernel<<<blocks_for(K), 256>>>(r.trans, cell, adj, K, m.d_dist);
+    {
+        std::vector<uint32_t> h(K);
+        for (int i = 0; i < K; i++) h[i] = i;
+        PPF_CUDA_TRY(cudaMemcpy(iota, h.data(), (size_t)K * 4, cudaMemcpyHostToDevice));
+    }
+    void *tmp = nullptr; size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, cell, shash, iota, sidx, K);
+    PPF_CUDA_TRY(cudaMalloc(&tmp, tb));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, cell, shash, iota, sidx, K));
+    // rot_clustering_kernel updates translations in place while neighbours read them (a race in the
+    // reference when use_averaged_clusters is set); we read a snapshot instead, which is deterministic.
+    PPF_CUDA_TRY(cudaMemcpyAsync(tin, r.trans, (size_t)K * sizeof(float3), cudaMemcpyDeviceToDevice, 0));
+    cluster_kernel<<<blocks_for(K), 256>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
+                                           m.d_dist, m.use_l1_norm, m.use_averaged_clusters);
+    argmax_kernel<<<1, 1024>>>(r.scores, K, d_arg);
+    PPF_CUDA_TRY(cudaGetLastError());
+    PPF_CUDA_TRY(cudaMemcpy(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost));
+    cudaFree(tmp); cudaFree(cell); cudaFree(adj); cudaFree(iota); cudaFree(shash); cudaFree(sidx);
+    cudaFree(tin); cudaFree(d_arg);
+    return PPF_OK;
+}
+
+}  // namespace ppf

@@ -1,0 +1,377 @@
+// ppf_vote.cu -- voting_scheme: scene pair generation + quantise + probe + Hough vote,
+// fused in one kernel, then threshold + ordering of the surviving votes.
+// Replaces Scene::Scene's ppf_kernel/ppf_hash_kernel pass (scene.cu:24-55),
+// ParallelHashArray::GetIndices (parallel_hash_array.hpp:81-92), ppf_vote_count_kernel,
+// ppf_vote_kernel (kernel.cu:480-554) and the sort/histogram/threshold tail of
+// Model::ComputeUniqueVotes (model.cu:148-170).
+//
+// The reference materialises N_s^2 features, N_s^2 keys, one 8-byte code per vote, and
+// sorts the codes.  Here nothing of size N_s^2 or #votes ever reaches HBM:
+//   * one CTA owns one (scene reference point s_r, model chunk c) pair and keeps the
+//     31 x chunk_rows accumulator of that reference point in shared memory;
+//   * phase 1 streams the scene points (coalesced float4 loads), computes the feature
+//     bins of (s_r, s_i), looks the cell up in the model's cell table and pushes the
+//     hits (bucket slice, alpha_s) into a shared-memory queue with one warp-aggregated
+//     atomic per warp;
+//   * phase 2 lets each warp drain hits: 32 lanes read 32 consecutive 4-byte bucket
+//     entries (one 128 B line), derive the alpha bin from two 19-bit binary angles and
+//     add to the shared accumulator with ATOMS.  A vote whose angle falls within a
+//     guard band of a bin edge recomputes alpha exactly as trans_model_scene does
+//     (kernel.cu:302-342), which keeps every count bit-exact;
+//   * phase 3 emits the cells that can still pass the reference's global threshold
+//     (count > thr * max, model.cu:164-167) using a monotone lower bound of the max.
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <vector>
+
+#include "../../include/ppf_b200.h"
+#include "ppf_internal.cuh"
+
+namespace ppf {
+
+struct VoteArgs {
+    // scene
+    const float4 *spos, *snrm, *sfy, *sfz;
+    int ns;
+    int ref_start, ref_stride, ref_count;         // s_r = ref_start + k*ref_stride
+    // model
+    const float4 *mpos, *mfy, *mfz;
+    int nm;
+    float d_dist, inv_d;
+    int K_d;
+    uint32_t U;
+    const uint32_t *cell2bucket;
+    const uint2 *ranges;
+    const uint32_t *entries, *map;
+    int n_chunks, chunk_rows;
+    // output
+    float thr;
+    int emit_all;                                 // 1: emit every non-zero cell (vote histogram)
+    unsigned long long *cand_codes;
+    uint32_t *cand_counts;
+    uint32_t cand_cap;
+    uint32_t *scalars;                            // [0]=cand_n [1]=max [2]=(unused) [3]=exact-alpha votes
+    unsigned long long *totals;                   // [0]=votes cast [1]=non-zero cells
+};
+
+__device__ __forceinline__ FrameYZ load_frame(const float4 *__restrict__ fy, const float4 *__restrict__ fz, int i) {
+    float4 y = __ldg(fy + i), z = __ldg(fz + i);
+    FrameYZ f;
+    f.y[0] = y.x; f.y[1] = y.y; f.y[2] = y.z; f.y[3] = y.w;
+    f.z[0] = z.x; f.z[1] = z.y; f.z[2] = z.z; f.z[3] = z.w;
+    return f;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);                       // [31][chunk_rows]
+    uint4 *queue = reinterpret_cast<uint4 *>(acc + kNAlphaBins * a.chunk_rows);   // [kHitQueue]
+    __shared__ uint32_t s_nhits, s_next, s_exact;
+    __shared__ uint32_t s_red[32];
+    __shared__ unsigned long long s_votes;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int chunk = blockIdx.x / a.ref_count;
+    const int refk = blockIdx.x - chunk * a.ref_count;
+    const int s_r = a.ref_start + refk * a.ref_stride;
+    const int C = a.chunk_rows;
+    const int chunk_base = chunk * C;
+    const uint2 *__restrict__ ranges = a.ranges + (size_t)chunk * a.U;
+
+    for (int i = tid; i < kNAlphaBins * C; i += THREADS) acc[i] = 0;
+    if (tid == 0) { s_exact = 0; s_votes = 0; }
+
+    // reference point (registers) and its local frame
+    PointN R;
+    {
+        float4 p = __ldg(a.spos + s_r), q = __ldg(a.snrm + s_r);
+        R.x = p.x; R.y = p.y; R.z = p.z; R.nx = q.x; R.ny = q.y; R.nz = q.z; R.nn = q.w;
+    }
+    const FrameYZ FS = load_frame(a.sfy, a.sfz, s_r);
+    unsigned long long my_votes = 0;
+    uint32_t my_exact = 0;
+
+    for (int base = 0; base < a.ns; base += kHitQueue) {
+        if (tid == 0) { s_nhits = 0; s_next = 0; }
+        __syncthreads();
+        // ---- phase 1: pairs (s_r, s_i) of this tile -> hit queue
+#pragma unroll 1
+        for (int it = 0; it < kHitQueue / THREADS; it++) {
+            const int i = base + it * THREADS + tid;
+            bool hit = false;
+            uint4 h = make_uint4(0, 0, 0, 0);
+            if (i < a.ns && i != s_r) {
+                float4 p = __ldg(a.spos + i), q = __ldg(a.snrm + i);
+                PointN O;
+                O.x = p.x; O.y = p.y; O.z = p.z; O.nx = q.x; O.ny = q.y; O.nz = q.z; O.nn = q.w;
+                FeatureBins fb = pair_feature_bins(R, O, a.d_dist, a.inv_d);
+                if (fb.kd >= 0 && fb.kd < a.K_d) {
+                    uint32_t b = __ldg(a.cell2bucket + cell_index(fb.kd, fb.k1, fb.k2, fb.k3));
+                    if (b != kNoBucket) {
+                        uint2 rg = __ldg(ranges + b);
+                        if (rg.y != 0) {
+                            float vy, vz;
+                            frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
+                            h = make_uint4(rg.x, rg.y, theta_code(vy, vz), (uint32_t)i);
+                            hit = true;
+                        }
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(&s_nhits, (uint32_t)__popc(m));
+                slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+                if (hit) queue[slot] = h;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: warps drain the queue; 32 lanes = 32 consecutive bucket entries
+        const uint32_t nhits = s_nhits;
+        while (true) {
+            uint32_t hi = 0;
+            if (lane == 0) hi = atomicAdd(&s_next, 1u);
+            hi = __shfl_sync(0xffffffffu, hi, 0);
+            if (hi >= nhits) break;
+            const uint4 h = queue[hi];
+            const uint32_t start = h.x, len = h.y, thv = h.z & kThetaMask, hslow = h.z >> 31;
+            if (lane == 0) my_votes += len;
+            const uint32_t *__restrict__ ent = a.entries + start;
+            for (uint32_t j0 = 0; j0 < len; j0 += 128) {
+                uint32_t e[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t j = j0 + u * 32 + lane;
+                    e[u] = (j < len) ? __ldg(ent + j) : 0xFFFFFFFFu;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    uint32_t j = j0 + u * 32 + lane;
+                    if (j < len) {
+                        const uint32_t loc = e[u] >> 20;
+                        uint32_t bin;
+                        bool ok = alpha_bin_fast(thv, (e[u] >> 1) & kThetaMask, bin);
+                        if (!ok || ((e[u] & 1u) | hslow)) {
+                            // exact alpha: rebuild u and v the way trans_model_scene does
+                            const uint32_t pidx = __ldg(a.map + start + j);
+                            const int m_r = chunk_base + (int)loc;
+                            const int m_i = (int)(pidx - (uint32_t)m_r * (uint32_t)a.nm);
+                            const FrameYZ FM = load_frame(a.mfy, a.mfz, m_r);
+                            const float4 mi = __ldg(a.mpos + m_i);
+                            const float4 si = __ldg(a.spos + h.w);
+                            float uy, uz, vy, vz;
+                            frame_apply_yz(FM, mi.x, mi.y, mi.z, uy, uz);
+                            frame_apply_yz(FS, si.x, si.y, si.z, vy, vz);
+                            bin = alpha_bin_exact(uy, uz, vy, vz);
+                            my_exact++;
+                        }
+                        atomicAdd(&acc[bin * C + loc], 1u);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- phase 3: block max, statistics, emission of candidate cells
+    uint32_t lmax = 0, nz = 0;
+    for (int i = tid; i < kNAlphaBins * C; i += THREADS) {
+        uint32_t c = acc[i];
+        lmax = max(lmax, c);
+        nz += (c != 0);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+        nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        my_exact += __shfl_xor_sync(0xffffffffu, my_exact, o);
+    }
+    if (lane == 0) {
+        s_red[warp] = lmax;
+        if (nz) atomicAdd(&a.totals[1], (unsigned long long)nz);
+        if (my_votes) atomicAdd(&s_votes, my_votes);
+        if (my_exact) atomicAdd(&s_exact, my_exact);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = (lane < THREADS / 32) ? s_red[lane] : 0;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if (lane == 0) {
+            uint32_t old = atomicMax(&a.scalars[1], v);
+            s_red[0] = max(old, v);
+            if (s_votes) atomicAdd(&a.totals[0], s_votes);
+            if (s_exact) atomicAdd(&a.scalars[3], s_exact);
+        }
+    }
+    __syncthreads();
+    const uint32_t bound = s_red[0];                       // <= final global max
+    if (bound == 0) return;
+    const float min_votecount = a.emit_all ? 0.0f : a.thr * (float)bound;     // model.cu:164
+    for (int i = tid; i < kNAlphaBins * C; i += THREADS) {
+        uint32_t c = acc[i];
+        if (c != 0 && (float)c > min_votecount) {
+            uint32_t bin = i / C, loc = i - bin * C;
+            uint32_t slot = atomicAdd(&a.scalars[0], 1u);
+            if (slot < a.cand_cap) {
+                // [scene ref : 32 | model point : 26 | alpha : 6]   (kernel.cu:548-549, model.h:61-63)
+                a.cand_codes[slot] = ((unsigned long long)(uint32_t)s_r << 32) |
+                                     (unsigned long long)((((uint32_t)chunk_base + loc) << 6) | bin);
+                a.cand_counts[slot] = c;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------
+__global__ void filter_kernel(const unsigned long long *codes, const uint32_t *counts, uint32_t n, float thr,
+                              uint32_t gmax, int emit_all, unsigned long long *ocodes, uint32_t *ocounts,
+                              uint32_t *on) {
+    float min_votecount = emit_all ? 0.0f : thr * (float)gmax;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t c = counts[i];
+        if ((float)c > min_votecount) {
+            uint32_t s = atomicAdd(on, 1u);
+            ocodes[s] = codes[i];
+            ocounts[s] = c;
+        }
+    }
+}
+
+static int ensure(void **p, size_t bytes) {
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess ? PPF_OK : PPF_ERR_CUDA;
+}
+
+void vote_result_free(VoteResult &r) {
+    cudaFree(r.cand_codes); cudaFree(r.cand_counts); cudaFree(r.scalars); cudaFree(r.votes_total);
+    cudaFree(r.codes); cudaFree(r.counts); cudaFree(r.transformations); cudaFree(r.weighted);
+    cudaFree(r.trans); cudaFree(r.rots); cudaFree(r.scores);
+    r = VoteResult();
+}
+
+int vote_reserve_K(VoteResult &r, size_t K) {
+    if (K <= r.cap_K && r.codes) return PPF_OK;
+    size_t cap = std::max<size_t>(K, 1024);
+    if (ensure((void **)&r.codes, cap * 8) || ensure((void **)&r.counts, cap * 4) ||
+        ensure((void **)&r.transformations, cap * 64) || ensure((void **)&r.weighted, cap * 4) ||
+        ensure((void **)&r.trans, cap * sizeof(float3)) || ensure((void **)&r.rots, cap * sizeof(float4)) ||
+        ensure((void **)&r.scores, cap * 4)) {
+        set_last_error("lookup: out of device memory for survivors");
+        return PPF_ERR_CUDA;
+    }
+    r.cap_K = cap;
+    return PPF_OK;
+}
+
+// Runs the fused vote kernel for the reference points of one shard.
+int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_rank, int shard_count, int emit_all,
+             VoteResult &r, unsigned long long *pairs_out, int *launches) {
+    if (df == 0 || shard_count < 1 || shard_rank < 0 || shard_rank >= shard_count) {
+        set_last_error("vote: ref_point_downsample_factor == 0 or bad shard");
+        return PPF_ERR_INVALID;
+    }
+    if (!r.scalars) {
+        PPF_CUDA_TRY(cudaMalloc(&r.scalars, 4 * sizeof(uint32_t)));
+        PPF_CUDA_TRY(cudaMalloc(&r.votes_total, 2 * sizeof(unsigned long long)));
+    }
+    if (!r.cand_codes) {
+        r.cand_cap = emit_all ? (size_t)1 << 24 : (size_t)1 << 22;
+        PPF_CUDA_TRY(cudaMalloc(&r.cand_codes, r.cand_cap * 8));
+        PPF_CUDA_TRY(cudaMalloc(&r.cand_counts, r.cand_cap * 4));
+    }
+    r.K = 0;
+    const int ns = scene.n;
+    // reference points: every df-th scene point (kernel.cu:432), then every shard_count-th of those
+    const int R_all = ns > 1 ? (ns + (int)df - 1) / (int)df : 0;     // ppf_kernel is a no-op for count <= 1
+    const int R = R_all > shard_rank ? (R_all - shard_rank + shard_count - 1) / shard_count : 0;
+    if (pairs_out) *pairs_out = (unsigned long long)R * (unsigned long long)ns;
+    if (launches) *launches = 0;
+    for (int attempt = 0; attempt < 8; attempt++) {
+        PPF_CUDA_TRY(cudaMemsetAsync(r.scalars, 0, 4 * sizeof(uint32_t), 0));
+        PPF_CUDA_TRY(cudaMemsetAsync(r.votes_total, 0, 2 * sizeof(unsigned long long), 0));
+        if (R == 0 || m.cloud.n <= 1 || m.K_d == 0) return PPF_OK;
+        VoteArgs a;
+        a.spos = scene.pos; a.snrm = scene.nrm; a.sfy = scene.fy; a.sfz = scene.fz; a.ns = ns;
+        a.ref_start = shard_rank * (int)df; a.ref_stride = shard_count * (int)df; a.ref_count = R;
+        a.mpos = m.cloud.pos; a.mfy = m.cloud.fy; a.mfz = m.cloud.fz; a.nm = m.cloud.n;
+        a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
+        a.cell2bucket = m.cell2bucket; a.ranges = m.ranges; a.entries = m.entries; a.map = m.map;
+        a.n_chunks = m.n_chunks; a.chunk_rows = m.chunk_rows;
+        a.thr = m.vote_count_threshold; a.emit_all = emit_all;
+        a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
+        a.scalars = r.scalars; a.totals = r.votes_total;
+        const size_t smem = (size_t)kNAlphaBins * m.chunk_rows * 4 + (size_t)kHitQueue * sizeof(uint4);
+        const long long grid = (long long)R * m.n_chunks;
+        if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, chunk) CTAs"); return PPF_ERR_UNSUPPORTED; }
+        if (smem > 113 * 1024) {
+            PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            vote_kernel<1024><<<(unsigned)grid, 1024, smem>>>(a);
+        } else {
+            PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            vote_kernel<512><<<(unsigned)grid, 512, smem>>>(a);
+        }
+        PPF_CUDA_TRY(cudaGetLastError());
+        if (launches) (*launches)++;
+        uint32_t h[4];
+        PPF_CUDA_TRY(cudaMemcpy(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+        if (h[0] <= r.cand_cap) return PPF_OK;
+        // candidate buffer too small: grow and vote again (results are deterministic)
+        r.cand_cap = (size_t)h[0] + (h[0] >> 2) + 1024;
+        cudaFree(r.cand_codes); cudaFree(r.cand_counts);
+        r.cand_codes = nullptr; r.cand_counts = nullptr;
+        PPF_CUDA_TRY(cudaMalloc(&r.cand_codes, r.cand_cap * 8));
+        PPF_CUDA_TRY(cudaMalloc(&r.cand_counts, r.cand_cap * 4));
+    }
+    set_last_error("vote: candidate buffer kept overflowing");
+    return PPF_ERR_CUDA;
+}
+
+// Threshold against the global maximum and order (count desc, code asc): the order that
+// thrust::sort + histogram + sort_by_key(greater<float>) leaves (model.cu:148-158; the
+// comparator sort is a stable merge sort, so equal counts stay in ascending code order).
+int order_survivors(VoteResult &r, size_t K, unsigned long long *codes_in, uint32_t *counts_in) {
+    if (K == 0) { r.K = 0; return PPF_OK; }
+    int rc = vote_reserve_K(r, K);
+    if (rc) return rc;
+    unsigned long long *c1 = nullptr; uint32_t *n1 = nullptr;
+    PPF_CUDA_TRY(cudaMalloc(&c1, K * 8));
+    PPF_CUDA_TRY(cudaMalloc(&n1, K * 4));
+    void *tmp = nullptr; size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, codes_in, c1, counts_in, n1, K);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb2, n1, r.counts, c1, r.codes, K);
+    PPF_CUDA_TRY(cudaMalloc(&tmp, std::max(tb, tb2)));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, codes_in, c1, counts_in, n1, K));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tb2, n1, r.counts, c1, r.codes, K));
+    PPF_CUDA_TRY(cudaDeviceSynchronize());
+    cudaFree(tmp); cudaFree(c1); cudaFree(n1);
+    r.K = K;
+    return PPF_OK;
+}
+
+int vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteResult &r) {
+    uint32_t h[4];
+    PPF_CUDA_TRY(cudaMemcpy(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+    uint32_t n = h[0];
+    r.K = 0;
+    if (n == 0 || global_max == 0) return PPF_OK;
+    unsigned long long *fc = nullptr; uint32_t *fn = nullptr, *d_on = nullptr;
+    PPF_CUDA_TRY(cudaMalloc(&fc, (size_t)n * 8));
+    PPF_CUDA_TRY(cudaMalloc(&fn, (size_t)n * 4));
+    PPF_CUDA_TRY(cudaMalloc(&d_on, 4));
+    PPF_CUDA_TRY(cudaMemset(d_on, 0, 4));
+    filter_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256>>>(r.cand_codes, r.cand_counts, n,
+                                                                         m.vote_count_threshold, global_max,
+                                                                         emit_all, fc, fn, d_on);
+    PPF_CUDA_TRY(cudaGetLastError());
+    uint32_t K = 0;
+    PPF_CUDA_TRY(cudaMemcpy(&K, d_on, 4, cudaMemcpyDeviceToHost));
+    int rc = order_survivors(r, K, fc, fn);
+    cudaFree(fc); cudaFree(fn); cudaFree(d_on);
+    return rc;
+}
+
+}  // namespace ppf
