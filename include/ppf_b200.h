@@ -128,6 +128,8 @@ int ppf_lookup_survivors(const ppf_lookup_t *lk, size_t *K, const uint64_t **cod
                          const uint32_t **counts_dev);
 int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const uint32_t *counts_dev,
                              size_t K);
+/* Device-to-device copy of the K survivors into caller-owned device buffers. */
+int ppf_lookup_copy_survivors(const ppf_lookup_t *lk, uint64_t *codes_dst_dev, uint32_t *counts_dst_dev);
 int ppf_lookup_poses(const ppf_model_t *model, const ppf_scene_t *scene, ppf_lookup_t *lk);
 int ppf_lookup_cluster(const ppf_model_t *model, ppf_lookup_t *lk);
 /* cpu_clustering = true variant: PCL-style greedy clustering of the survivors on one host

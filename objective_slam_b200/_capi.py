@@ -1,7 +1,7 @@
 """ctypes bindings for lib/libppf_b200.so (the C ABI of include/ppf_b200.h).
 
 There is deliberately no fallback: if the CUDA library is missing or fails to load,
-importing this module raises.  The oracle (oracle/) is never imported from here.
+importing this module raises.  Test oracles are never imported from here.
 """
 from __future__ import annotations
 
@@ -22,6 +22,7 @@ EXPORTS = [
     "ppf_model_table_get", "ppf_model_features",
     "ppf_lookup_create", "ppf_lookup_destroy", "ppf_model_lookup", "ppf_lookup_vote",
     "ppf_lookup_local_max", "ppf_lookup_finalize", "ppf_lookup_survivors", "ppf_lookup_set_survivors",
+    "ppf_lookup_copy_survivors",
     "ppf_lookup_poses", "ppf_lookup_cluster", "ppf_lookup_cluster_cpu", "ppf_lookup_get_stats",
     "ppf_lookup_get", "ppf_vote_histogram", "ppf_registration",
 ]
@@ -88,6 +89,7 @@ def _load():
     L.ppf_lookup_finalize.argtypes = [vp, u32, vp]
     L.ppf_lookup_survivors.argtypes = [vp, P(sz), P(vp), P(vp)]
     L.ppf_lookup_set_survivors.argtypes = [vp, vp, vp, sz]
+    L.ppf_lookup_copy_survivors.argtypes = [vp, vp, vp]
     L.ppf_lookup_poses.argtypes = [vp, vp, vp]
     L.ppf_lookup_cluster.argtypes = [vp, vp]
     L.ppf_lookup_cluster_cpu.argtypes = [vp, vp, vp]

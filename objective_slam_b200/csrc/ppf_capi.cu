@@ -173,6 +173,14 @@ int ppf_lookup_survivors(const ppf_lookup_t *lk, size_t *K, const uint64_t **cod
     return PPF_OK;
 }
 
+int ppf_lookup_copy_survivors(const ppf_lookup_t *lk, uint64_t *codes_dst_dev, uint32_t *counts_dst_dev) {
+    PPF_CHECK_ARG(lk && (lk->res.K == 0 || (codes_dst_dev && counts_dst_dev)), "copy_survivors: NULL argument");
+    if (lk->res.K == 0) return PPF_OK;
+    PPF_CUDA_TRY(cudaMemcpy(codes_dst_dev, lk->res.codes, lk->res.K * 8, cudaMemcpyDeviceToDevice));
+    PPF_CUDA_TRY(cudaMemcpy(counts_dst_dev, lk->res.counts, lk->res.K * 4, cudaMemcpyDeviceToDevice));
+    return PPF_OK;
+}
+
 int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const uint32_t *counts_dev, size_t K) {
     PPF_CHECK_ARG(lk && (K == 0 || (codes_dev && counts_dev)), "set_survivors: NULL argument");
     unsigned long long *c = nullptr; uint32_t *n = nullptr;

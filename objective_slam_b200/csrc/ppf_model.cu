@@ -11,6 +11,7 @@
 //  * the vote payload (chunk-local m_r, alpha_m as a 19-bit binary angle) is
 //    gathered into bucket order once, so voting streams 4 B per vote.
 #include <cub/cub.cuh>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/ppf_b200.h"
@@ -255,7 +256,12 @@ int model_build(ModelTable &m) {
     }
     if (!(m.d_dist > 0.f)) { set_last_error("model: d_dist must be > 0"); return PPF_ERR_INVALID; }
     m.inv_d_dist = 1.0f / m.d_dist;
-    m.n_chunks = std::max(1, (n + kMaxChunkRows - 1) / kMaxChunkRows);
+    int max_rows = kMaxChunkRows;
+    if (const char *e = getenv("PPF_B200_CHUNK_ROWS")) {        // test hook: force more / smaller chunks
+        int v = atoi(e);
+        if (v >= 32 && v <= kMaxChunkRows) max_rows = v / 32 * 32;
+    }
+    m.n_chunks = std::max(1, (n + max_rows - 1) / max_rows);
     m.chunk_rows = std::max(32, (((n + m.n_chunks - 1) / m.n_chunks) + 31) / 32 * 32);
     PPF_CUDA_TRY(cudaMalloc(&m.weights, std::max(1, n) * sizeof(float)));
     if (n > 0) fill_kernel<<<(n + 255) / 256, 256>>>(m.weights, n, 1.0f);

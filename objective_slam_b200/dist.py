@@ -1,0 +1,91 @@
+"""Multi-GPU recognition: scene reference points sharded over the ranks of one node.
+
+Every scene reference point owns an independent accumulator (the high 32 bits of a vote code are
+s_r, model.h:61-63), so voting needs no data-path collective: rank r votes for every world-th
+reference point against a replicated model table.  Only two tiny exchanges couple the ranks, both
+required by the reference's semantics (model.cu:160-170):
+  1. all_reduce(MAX) of the largest accumulator cell -> the global threshold count > thr * max;
+  2. all_gather of each rank's surviving (code, count) list (exact parity needs every survivor,
+     not a truncated top-k), after which pose computation and clustering run replicated.
+One process per GPU, torch.distributed over NCCL (gloo on CPU for the tests).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.distributed as dist
+
+from . import _capi as C
+
+
+def shard_reference_points(n_scene: int, ref_df: int, rank: int, world: int):
+    """Scene reference points of one rank: every world-th of the points with s_r % ref_df == 0."""
+    refs = range(0, n_scene if n_scene > 1 else 0, ref_df)
+    return list(refs)[rank::world]
+
+
+def merge_survivors(codes: torch.Tensor, counts: torch.Tensor, local_max: int, thr: float, group=None):
+    """codes int64 (the 64-bit vote codes), counts int32: this rank's candidates (any superset of its
+    survivors).  Returns (codes, counts, global_max) of ALL ranks' survivors, identical on every rank,
+    ordered (count desc, code asc) like the reference leaves them (model.cu:148-170)."""
+    dev = codes.device
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    gmax = torch.tensor([int(local_max)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    g = int(gmax.item())
+    # float compare exactly as the reference: (float)count > thr * (float)max
+    min_votecount = torch.tensor(thr, dtype=torch.float32) * torch.tensor(g, dtype=torch.float32)
+    keep = counts.to(torch.float32) > min_votecount.to(dev)
+    codes, counts = codes[keep].contiguous(), counts[keep].to(torch.int32).contiguous()
+    if world > 1:
+        n = torch.tensor([codes.numel()], dtype=torch.int64, device=dev)
+        ns = [torch.zeros_like(n) for _ in range(world)]
+        dist.all_gather(ns, n, group=group)
+        ns = [int(x.item()) for x in ns]
+        cap = max(max(ns), 1)
+        pc = torch.zeros(cap, dtype=torch.int64, device=dev)
+        pn = torch.zeros(cap, dtype=torch.int32, device=dev)
+        pc[: codes.numel()] = codes
+        pn[: counts.numel()] = counts
+        gc = [torch.empty_like(pc) for _ in range(world)]
+        gn = [torch.empty_like(pn) for _ in range(world)]
+        dist.all_gather(gc, pc, group=group)
+        dist.all_gather(gn, pn, group=group)
+        codes = torch.cat([c[:k] for c, k in zip(gc, ns)])
+        counts = torch.cat([c[:k] for c, k in zip(gn, ns)])
+    # (count desc, code asc). Codes are compared as unsigned: flip the sign bit for the signed sort.
+    if codes.numel():
+        key = codes ^ torch.tensor(-0x8000000000000000, dtype=torch.int64, device=dev)
+        order = torch.argsort(key, stable=True)
+        codes, counts = codes[order], counts[order]
+        order = torch.argsort(counts.to(torch.int64), descending=True, stable=True)
+        codes, counts = codes[order], counts[order]
+    return codes, counts, g
+
+
+def lookup_sharded(model, scene, lookup, rank: int, world: int, group=None, arrays: bool = False):
+    """Model::ppf_lookup over `world` GPUs; returns the same LookupResult on every rank."""
+    df = scene.ref_point_downsample_factor
+    C.check(C.lib.ppf_lookup_vote(model._h, scene._h, df, rank, world, lookup._h))
+    lmax = ctypes.c_uint32()
+    C.check(C.lib.ppf_lookup_local_max(lookup._h, ctypes.byref(lmax)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    gmax = torch.tensor([lmax.value], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
+    g = int(gmax.item())
+    C.check(C.lib.ppf_lookup_finalize(model._h, g, lookup._h))        # local filter with the global max
+    if world > 1:
+        K = ctypes.c_size_t()
+        C.check(C.lib.ppf_lookup_survivors(lookup._h, ctypes.byref(K), None, None))
+        codes = torch.empty(max(K.value, 1), dtype=torch.int64, device=dev)
+        counts = torch.empty(max(K.value, 1), dtype=torch.int32, device=dev)
+        C.check(C.lib.ppf_lookup_copy_survivors(lookup._h, codes.data_ptr(), counts.data_ptr()))
+        codes, counts, _ = merge_survivors(codes[: K.value], counts[: K.value], g, model.vote_count_threshold, group)
+        torch.cuda.synchronize()
+        C.check(C.lib.ppf_lookup_set_survivors(lookup._h, codes.data_ptr(), counts.data_ptr(), codes.numel()))
+    C.check(C.lib.ppf_lookup_poses(model._h, scene._h, lookup._h))
+    C.check(C.lib.ppf_lookup_cluster(model._h, lookup._h))
+    return lookup.result(arrays=arrays)

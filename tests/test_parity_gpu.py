@@ -1,0 +1,163 @@
+"""Parity proper: libppf_b200 (through the C ABI) against the reference's own CUDA kernels
+(oracle/_ref: kernel.cu + parallel_hash_array.hpp compiled for sm_100a, replayed by
+oracle/ref_harness.cu) on the same seeded inputs.  Everything is compared BIT-EXACTLY: quantised
+features, keys, hash-table arrays, every accumulator cell, survivors and their order, poses,
+quaternions, cluster scores, winner.  (The north star only asks 1e-4 for poses; we get 0.)"""
+import numpy as np
+import pytest
+
+from conftest import golden, have_ref
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not have_ref(), reason="oracle/_ref missing")]
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def clouds(nm, ns, tau=0.05, seed=0, kind="lumpy"):
+    from objective_slam_b200 import synth
+    mp, mn = synth.make_model(nm, seed=100 + seed)
+    if kind == "lumpy":
+        sp, sn, T = synth.make_scene(mp, mn, ns, seed=200 + seed)
+    elif kind == "lattice":       # TSDF-like lattice, axis-aligned normals: exact zeros everywhere
+        sp, sn = synth.make_lattice_scene(ns, pitch=2.5, seed=seed)
+        mp, mn = synth.make_lattice_scene(nm, pitch=2.5, seed=seed + 1)
+        T = np.eye(4)
+    elif kind == "degenerate":    # duplicate points, zero / parallel normals, coincident pairs
+        sp, sn, T = synth.make_scene(mp, mn, ns, seed=200 + seed)
+        sp[5] = sp[6]; sn[7] = 0; sn[8] = sn[9]; sp[10] = sp[11]; sn[10] = sn[11]
+        mp[3] = mp[4]; mn[5] = 0; mn[6] = mn[7] = np.array([0, 0, 1], np.float32)
+        sn[12] = np.array([1, 0, 0], np.float32); sn[13] = np.array([0, 1, 0], np.float32)
+        sn[14] = np.array([0, -1, 0], np.float32); sn[15] = np.array([-1, 0, 0], np.float32)
+    return mp, mn, sp, sn, synth.d_dist_for(mp, tau), T
+
+
+def compare_all(mp, mn, sp, sn, d, df, thr=0.4, l1=False, avg=False, check_hist=True):
+    import objective_slam_b200 as ppf
+    from oracle import refgpu
+    rm = refgpu.RefModel(mp, mn, d); rs = refgpu.RefScene(sp, sn, d, df)
+    m = ppf.Model(mp, mn, d, thr, use_l1_norm=l1, use_averaged_clusters=avg); s = ppf.Scene(sp, sn, d, df)
+    # point_pair_feature / my_discretize / hash
+    rp, rk = rs.features(); p, k = s.features()
+    assert (bits(rp) == bits(p)).all(), "scene quantised features"
+    assert (rk == k).all(), "scene keys"
+    pm, km = m.features()
+    assert (bits(rm.features()) == bits(pm)).all(), "model quantised features"
+    # model_description
+    for name, a, b in zip(("hashkeys", "counts", "first", "map"), rm.table(), m.table()):
+        assert a.shape == b.shape and (a == b).all(), f"table {name}"
+    # voting_scheme: every accumulator cell
+    if check_hist:
+        rc, rn = rm.vote_histogram(rs); c, n = m.vote_histogram(s)
+        assert rc.shape == c.shape and (rc == c).all() and (rn == n).all(), "vote histogram"
+    r = rm.lookup(rs, thr, l1, avg); q = m.ppf_lookup(s)
+    assert r["num_nonunique_votes"] == q.num_nonunique_votes
+    assert r["num_unique_votes"] == q.num_unique_votes
+    if r["K"] < 0:
+        assert q.num_top_votes == 0 and q.status != 0
+        return r, q
+    assert r["K"] == q.num_top_votes
+    assert (r["votes"] == q.votes).all() and (r["counts"] == q.voteCounts).all(), "survivors / order"
+    assert (bits(r["transformations"]) == bits(q.transformations)).all(), "poses"
+    assert (bits(r["weighted"]) == bits(q.weightedVoteCounts)).all()
+    assert (bits(r["rots"]) == bits(q.transformation_rots)).all(), "quaternions"
+    if not avg:       # the reference's in-place averaging races (kernel.cu:758 vs :742,750)
+        assert (bits(r["trans"]) == bits(q.transformation_trans)).all()
+        assert (bits(r["scores"]) == bits(q.vote_counts_out)).all(), "cluster scores"
+        assert r["max_idx"] == q.max_idx
+        assert (bits(r["pose"]) == bits(q.pose)).all(), "final pose"
+    return r, q
+
+
+@pytest.mark.parametrize("nm,ns,df,tau", [(300, 500, 1, 0.05), (300, 500, 5, 0.05), (257, 333, 3, 0.1),
+                                          (640, 1500, 1, 0.05), (1000, 1000, 5, 0.05), (33, 2100, 7, 0.05)])
+def test_stagewise_parity(nm, ns, df, tau):
+    mp, mn, sp, sn, d, _ = clouds(nm, ns, tau, seed=nm + ns)
+    compare_all(mp, mn, sp, sn, d, df)
+
+
+@pytest.mark.parametrize("kind", ["lattice", "degenerate"])
+@pytest.mark.parametrize("df", [1, 4])
+def test_degenerate_inputs(kind, df):
+    """NaN features (acos > 1, 0/0), coincident points, zero normals, exact zeros / signed zeros."""
+    mp, mn, sp, sn, d, _ = clouds(200, 420, 0.08, seed=5, kind=kind)
+    r, q = compare_all(mp, mn, sp, sn, d, df)
+    assert q.num_nonunique_votes > 0
+
+
+def test_model_split_into_several_chunks(monkeypatch):
+    """2000-point model -> two accumulator chunks; forced 64-row chunks -> 8 chunks.  Same answers."""
+    mp, mn, sp, sn, d, _ = clouds(2000, 700, 0.05, seed=9)
+    compare_all(mp, mn, sp, sn, d, 5, check_hist=False)
+    monkeypatch.setenv("PPF_B200_CHUNK_ROWS", "64")
+    mp, mn, sp, sn, d, _ = clouds(500, 600, 0.05, seed=10)
+    compare_all(mp, mn, sp, sn, d, 2)
+
+
+@pytest.mark.parametrize("l1,avg,thr", [(True, False, 0.4), (False, True, 0.4), (False, False, 0.9), (False, False, 0.0)])
+def test_lookup_options(l1, avg, thr):
+    mp, mn, sp, sn, d, _ = clouds(250, 400, 0.06, seed=21)
+    compare_all(mp, mn, sp, sn, d, 2, thr=thr, l1=l1, avg=avg, check_hist=False)
+
+
+@pytest.mark.parametrize("nm,ns", [(1, 50), (2, 50), (50, 1), (50, 2), (3, 3)])
+def test_tiny_and_ragged_sizes(nm, ns):
+    """count <= 1 makes every reference kernel a no-op (kernel.cu:406,461,...); K <= 1 gives a zero pose."""
+    mp, mn, sp, sn, d, _ = clouds(60, 60, 0.1, seed=3)
+    compare_all(mp[:nm], mn[:nm], sp[:ns], sn[:ns], d, 1)
+
+
+def test_scene_far_from_model_has_no_votes():
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, _ = clouds(100, 100, 0.05, seed=4)
+    far = (sp * 1000).astype(np.float32)                     # every scene pair is longer than any model pair
+    r = ppf.Model(mp, mn, d).ppf_lookup(ppf.Scene(far, sn, d, 1))
+    assert r.status == 4 and r.num_nonunique_votes == 0 and r.num_top_votes == 0 and not r.pose.any()
+
+
+@pytest.mark.parametrize("name", ["tiny_df1", "tiny_df3"])
+def test_golden(name):
+    """Against the committed fixtures (reference kernels on a B200, tests/golden/make_golden.py)."""
+    import objective_slam_b200 as ppf
+    g = golden(name)
+    d, df = float(g["d_dist"]), int(g["ref_df"])
+    m = ppf.Model(g["model_pts"], g["model_nrm"], d); s = ppf.Scene(g["scene_pts"], g["scene_nrm"], d, df)
+    p, k = s.features()
+    assert (bits(p) == bits(g["scene_ppf"])).all() and (k == g["scene_keys"]).all()
+    hk, cnt, first, mapp = m.table()
+    assert (hk == g["hashkeys"]).all() and (cnt == g["counts"]).all() and (mapp == g["map"]).all()
+    c, n = m.vote_histogram(s)
+    assert (c == g["hist_codes"]).all() and (n == g["hist_counts"]).all()
+    q = m.ppf_lookup(s)
+    assert (q.votes == g["votes"]).all() and (q.voteCounts == g["vote_counts"]).all()
+    assert (bits(q.transformations) == bits(g["transformations"])).all()
+    assert (bits(q.vote_counts_out) == bits(g["scores"])).all() and q.max_idx == int(g["max_idx"])
+    assert (bits(q.pose) == bits(g["pose"])).all()
+
+
+def test_registration_boundary():
+    """ppf_registration (ppf.h:9-15): 2 scenes x 2 models with different d_dist, host clouds in, poses out."""
+    import objective_slam_b200 as ppf
+    from oracle import refgpu
+    mpa, mna, spa, sna, da, _ = clouds(220, 380, 0.05, seed=31)
+    mpb, mnb, spb, snb, db, _ = clouds(180, 300, 0.07, seed=32)
+    poses, status = ppf.ppf_registration([(spa, sna), (spb, snb)], [(mpa, mna), (mpb, mnb)], [da, db],
+                                         ref_point_downsample_factor=3, devUse=1)
+    for i, (sp, sn) in enumerate([(spa, sna), (spb, snb)]):
+        for j, (mp, mn, d) in enumerate([(mpa, mna, da), (mpb, mnb, db)]):
+            r = refgpu.RefModel(mp, mn, d).lookup(refgpu.RefScene(sp, sn, d, 3))
+            if r["K"] > 0:
+                assert status[i, j] == 0 and (bits(r["pose"]) == bits(poses[i, j])).all()
+            else:
+                assert not poses[i, j].any()
+
+
+def test_device_resident_clouds_match_host_clouds():
+    import torch
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, _ = clouds(200, 300, 0.05, seed=41)
+    a = ppf.Model(mp, mn, d).ppf_lookup(ppf.Scene(sp, sn, d, 2))
+    t = lambda x: torch.from_numpy(x).cuda()
+    b = ppf.Model(t(mp), t(mn), d).ppf_lookup(ppf.Scene(t(sp), t(sn), d, 2))
+    assert (a.votes == b.votes).all() and (a.voteCounts == b.voteCounts).all() and (bits(a.pose) == bits(b.pose)).all()

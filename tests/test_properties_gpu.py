@@ -1,0 +1,104 @@
+"""Size-independent properties of the CUDA path at sizes the reference cannot run (it needs ~60*N_s^2
+bytes and overflows int at N > 46,340): sharding invariance, chunking invariance, determinism,
+rigid-transform recovery (the reference's own acceptance test, alignment.cpp:317-323)."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(nm, ns, seed=0):
+    from objective_slam_b200 import synth
+    mp, mn = synth.make_model(nm, seed=synth.SEED_BASE + seed)
+    sp, sn, T = synth.make_scene(mp, mn, ns, seed=synth.SEED_BASE + seed + 1)
+    return mp, mn, sp, sn, synth.d_dist_for(mp), T
+
+
+def _ht_dist(A, B):
+    """linalg.cu:9-20: (|dt|, |angle|) between two 4x4 poses."""
+    dt = np.linalg.norm(A[:3, 3] - B[:3, 3])
+    R = A[:3, :3].T @ B[:3, :3]
+    ang = np.arccos(np.clip((np.trace(R) - 1) / 2, -1, 1))
+    return dt, abs(ang)
+
+
+@pytest.mark.parametrize("nm,ns,df", [(2000, 16000, 5), (10000, 50000, 50)])
+def test_rigid_transform_recovery(nm, ns, df):
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, T = _case(nm, ns, seed=nm)
+    r = ppf.Model(mp, mn, d).ppf_lookup(ppf.Scene(sp, sn, d, df), arrays=False)
+    dt, ang = _ht_dist(r.pose.astype(np.float64), T)
+    assert dt < 0.1 * 100.0 and ang < np.radians(12), (dt, ang)      # alignment.cpp:141-144 defaults
+    assert r.num_scene_pairs == ((ns + df - 1) // df) * ns
+
+
+def test_sharding_is_invariant():
+    """Votes of 4 shards of the reference points add up to the unsharded run; survivors are identical."""
+    import objective_slam_b200 as ppf
+    from objective_slam_b200 import _capi as C
+    mp, mn, sp, sn, d, _ = _case(1500, 6000, seed=7)
+    m, s = ppf.Model(mp, mn, d), ppf.Scene(sp, sn, d, 3)
+    whole = m.ppf_lookup(s)
+    lk = ppf.Lookup()
+    votes = cells = pairs = 0
+    gmax = 0
+    for r in range(4):
+        C.check(C.lib.ppf_lookup_vote(m._h, s._h, 3, r, 4, lk._h))
+        st = lk.stats()
+        votes += st.num_nonunique_votes; cells += st.num_unique_votes; pairs += st.num_scene_pairs
+        gmax = max(gmax, st.max_vote_count)
+    assert (votes, cells, pairs, gmax) == (whole.num_nonunique_votes, whole.num_unique_votes,
+                                           whole.num_scene_pairs, whole.max_vote_count)
+    surv = {}
+    for r in range(4):
+        C.check(C.lib.ppf_lookup_vote(m._h, s._h, 3, r, 4, lk._h))
+        C.check(C.lib.ppf_lookup_finalize(m._h, gmax, lk._h))
+        C.check(C.lib.ppf_lookup_poses(m._h, s._h, lk._h)); C.check(C.lib.ppf_lookup_cluster(m._h, lk._h))
+        part = lk.result()
+        surv.update(zip(part.votes.tolist(), part.voteCounts.tolist()))
+    assert surv == dict(zip(whole.votes.tolist(), whole.voteCounts.tolist()))
+
+
+def test_chunking_is_invariant_and_runs_are_deterministic(monkeypatch):
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, _ = _case(3000, 5000, seed=3)
+    s = ppf.Scene(sp, sn, d, 10)
+    a = ppf.Model(mp, mn, d).ppf_lookup(s)
+    b = ppf.Model(mp, mn, d).ppf_lookup(s)
+    monkeypatch.setenv("PPF_B200_CHUNK_ROWS", "416")
+    c = ppf.Model(mp, mn, d).ppf_lookup(s)
+    for x in (b, c):
+        assert (a.votes == x.votes).all() and (a.voteCounts == x.voteCounts).all()
+        assert a.num_nonunique_votes == x.num_nonunique_votes and a.num_unique_votes == x.num_unique_votes
+        assert (a.pose.view(np.uint32) == x.pose.view(np.uint32)).all() and a.max_idx == x.max_idx
+
+
+def test_histogram_checksum_and_model_reuse():
+    """sum of all accumulator cells == votes cast; one model handle serves many scenes."""
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, _ = _case(400, 900, seed=11)
+    m = ppf.Model(mp, mn, d)
+    for df in (1, 2, 9):
+        s = ppf.Scene(sp, sn, d, df)
+        codes, counts = m.vote_histogram(s)
+        r = m.ppf_lookup(s)
+        assert int(counts.astype(np.int64).sum()) == r.num_nonunique_votes and len(codes) == r.num_unique_votes
+        assert (np.diff(codes.astype(np.int64)) > 0).all()
+        assert int(counts.max()) == r.max_vote_count == int(r.voteCounts[0])
+        assert ((codes >> np.uint64(32)).astype(np.int64) % df == 0).all()      # only reference rows vote
+        assert ((codes & np.uint64(63)) <= 30).all()                               # alpha_idx in [0, 30]
+
+
+def test_cpu_clustering_variant_agrees_with_gpu_clustering():
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, T = _case(1200, 3000, seed=13)
+    s = ppf.Scene(sp, sn, d, 5)
+    a = ppf.Model(mp, mn, d).ppf_lookup(s, arrays=False)
+    b = ppf.Model(mp, mn, d, cpu_clustering=True).ppf_lookup(s, arrays=False)
+    for r in (a, b):
+        dt, ang = _ht_dist(r.pose.astype(np.float64), T)
+        assert dt < 10.0 and ang < np.radians(12)
+    assert abs(np.linalg.det(b.pose[:3, :3].astype(np.float64)) - 1) < 1e-4
