@@ -60,6 +60,8 @@ typedef struct ppf_lookup ppf_lookup_t;
 
 const char *ppf_last_error(void);
 const char *ppf_version(void);
+/* Number of kernels of this library launched by the process so far (diagnostic; bench.py's gpu_launches). */
+uint64_t ppf_kernel_launch_count(void);
 
 /* ---- Scene ------------------------------------------------------------------ */
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n,

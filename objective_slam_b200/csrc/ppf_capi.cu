@@ -1,6 +1,7 @@
 // ppf_capi.cu -- the C ABI declared in include/ppf_b200.h (handles, error strings,
 // staging of the lookup stages, and the ppf_registration drop-in boundary).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <string>
@@ -12,6 +13,8 @@
 namespace ppf {
 static thread_local std::string g_last_error;
 void set_last_error(const std::string &msg) { g_last_error = msg; }
+static std::atomic<unsigned long long> g_kernel_launches{0};
+void count_launch(int n) { g_kernel_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 }  // namespace ppf
 
 using namespace ppf;
@@ -50,6 +53,7 @@ extern "C" {
 
 const char *ppf_last_error(void) { return g_last_error.c_str(); }
 const char *ppf_version(void) { return "ppf_b200 0.1 (sm_100a)"; }
+uint64_t ppf_kernel_launch_count(void) { return g_kernel_launches.load(); }
 
 // ---- Scene ------------------------------------------------------------------------
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem,

@@ -10,7 +10,7 @@
 //   ModelTable hashkeys[U] counts[U] first[U] map[N*N]  -- the reference's ParallelHashArray contents
 //                                                          (parallel_hash_array.hpp:36-46) as u32
 //              entries[N*N] u32                         -- voting payload in bucket order:
-//                                                          [m_r - chunk_base : 12 | theta_u : 19 | slow : 1]
+//                                                          [slow : 1 | theta_u : 19 | m_r - chunk_base : 12]
 //              ranges[n_chunks][U] uint2                -- (start, len) of the part of bucket b whose model
 //                                                          reference points fall in chunk c (buckets ascend in
 //                                                          m_r, so every chunk is one contiguous slice)
@@ -26,9 +26,13 @@
 namespace ppf {
 
 // Shared-memory vote accumulator geometry: 31 alpha bins x chunk_rows u32 counters.
-constexpr int kMaxChunkRows = 1536;          // 31 * 1536 * 4 B = 190,464 B
-constexpr int kHitQueue     = 2048;          // 16 B each
-constexpr int kModelLocBits = 12;
+constexpr int kMaxChunkRows = 1504;          // (31 * (1504 + 1) + 1) * 4 B = 186,624 B
+constexpr int kHitQueue     = 2048;          // 16 B record + 4 B cursor each
+constexpr int kVoteSegment  = 512;           // bucket entries one warp takes per grab (16 per lane)
+// accumulator row stride: chunk_rows is a multiple of 32, so +1 makes bank = (bin + row) mod 32 --
+// lanes that hit the same model point with different alpha bins (the common case inside a bucket,
+// whose entries are sorted by m_r) fall into different banks.
+__host__ __device__ constexpr int acc_stride(int chunk_rows) { return chunk_rows + 1; }
 
 struct Cloud {
     int n = 0;
@@ -83,6 +87,9 @@ void set_last_error(const std::string &msg);
             return PPF_ERR_CUDA;                                                           \
         }                                                                                  \
     } while (0)
+
+// every launch of one of OUR kernels is counted (bench.py reports it as gpu_launches)
+void count_launch(int n = 1);
 
 // ---- entry points of the translation units -------------------------------------------
 int  cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, Cloud &c);

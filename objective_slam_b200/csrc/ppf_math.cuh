@@ -280,14 +280,31 @@ __device__ __forceinline__ uint32_t alpha_bin_exact(float uy, float uz, float vy
     return (uint32_t)quant_bin(a2, d_angle0(), 4.7746482f);
 }
 
-// Fast alpha bin from two binary angles; returns true when the result is
-// provably the reference's bin (outside the guard band around bin edges).
-__device__ __forceinline__ bool alpha_bin_fast(uint32_t theta_v, uint32_t theta_u, uint32_t &bin) {
-    uint32_t t = (theta_v - theta_u + kThetaHalf) & kThetaMask;   // (alpha + pi) / 2pi * 2^19
-    uint32_t x = t * (uint32_t)kNAngle;
-    bin = x >> kThetaBits;
-    uint32_t frac = x & kThetaMask;
-    return (frac - kAlphaGuard) < (kThetaMask + 1u - 2u * kAlphaGuard);
+// ---- packed voting payload ------------------------------------------------------------------
+// bucket entry (model pair):  [slow : 1 | theta_u : 19 | m_r - chunk_base : 12]
+// hit word     (scene pair):  [slow : 1 | (theta_v + half) mod 2^19 : 19 | 0 : 12]
+constexpr int      kLocBits   = 12;
+constexpr uint32_t kLocMask   = (1u << kLocBits) - 1u;
+constexpr uint32_t kThetaFld  = kThetaMask << kLocBits;          // 0x7FFFF000
+constexpr uint32_t kGuardLo   = kAlphaGuard << (32 - kThetaBits); // guard band in units of frac << 13
+
+__host__ __device__ __forceinline__ uint32_t pack_entry(uint32_t loc, uint32_t theta_code_u) {
+    return (theta_code_u & 0x80000000u) | ((theta_code_u & kThetaMask) << kLocBits) | loc;
+}
+__host__ __device__ __forceinline__ uint32_t pack_hit_theta(uint32_t theta_code_v) {
+    return (theta_code_v & 0x80000000u) | ((((theta_code_v & kThetaMask) + kThetaHalf) & kThetaMask) << kLocBits);
+}
+// Fast alpha bin: t = (theta_v - theta_u + half) mod 2^19 = (alpha + pi)/2pi * 2^19, bin = floor(30 t / 2^19).
+// With t held as t << 12, (t << 12) * 60 = (30 t) << 13: the high word is the bin, the low word the
+// fractional position inside the bin (<< 13).  `hit_theta_ones` is the hit word with its low 12 bits
+// set, so that subtracting the whole entry cannot borrow out of the m_r field; bit 31 (slow flag) only
+// disturbs bit 31 of the difference, which the mask drops.  Returns true when the bin is provably the
+// reference's: fraction outside the guard band around both bin edges and entry not flagged slow.
+__device__ __forceinline__ bool alpha_bin_fast(uint32_t hit_theta_ones, uint32_t entry, uint32_t &bin) {
+    const uint32_t t12 = (hit_theta_ones - entry) & kThetaFld;
+    bin = __umulhi(t12, 2u * kNAngle);
+    const uint32_t lo = t12 * (2u * kNAngle) + kGuardLo;
+    return (lo >= 2u * kGuardLo) && ((int32_t)entry >= 0);
 }
 
 }  // namespace ppf

@@ -63,6 +63,7 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
         dx = tmpx; dn = tmpn;
     }
     pack_cloud_kernel<<<(n + 255) / 256, 256>>>(dx, xs, dn, ns, n, c.pos, c.nrm, c.fy, c.fz);
+    count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     if (tmpx) { PPF_CUDA_TRY(cudaStreamSynchronize(0)); cudaFree(tmpx); cudaFree(tmpn); }
     return PPF_OK;
@@ -123,6 +124,7 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
     if (keys_host) PPF_CUDA_TRY(cudaMalloc(&dk, total * sizeof(uint32_t)));
     int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     features_tile_kernel<<<blocks, 256>>>(c.pos, c.nrm, c.n, d_dist, 1.0f / d_dist, df, rb, re, ob, oe, dp, dk);
+    count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     if (dp) PPF_CUDA_TRY(cudaMemcpy(ppfs_host, dp, total * sizeof(float4), cudaMemcpyDeviceToHost));
     if (dk) PPF_CUDA_TRY(cudaMemcpy(keys_host, dk, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -176,7 +178,7 @@ __global__ void iota_kernel(uint32_t *v, size_t n) {
         v[i] = (uint32_t)i;
 }
 
-// entries[q] = [m_r - chunk_base : 12 | theta : 19 | slow : 1] for sorted position q
+// entries[q] = [slow : 1 | theta : 19 | m_r - chunk_base : 12] for sorted position q
 __global__ void gather_entries_kernel(const uint32_t *__restrict__ map, const uint32_t *__restrict__ theta,
                                       size_t total, int n, int chunk_rows, uint32_t *entries) {
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
@@ -184,7 +186,7 @@ __global__ void gather_entries_kernel(const uint32_t *__restrict__ map, const ui
         uint32_t th = __ldg(theta + p);
         uint32_t r = p / (uint32_t)n;
         uint32_t loc = r % (uint32_t)chunk_rows;
-        entries[q] = (loc << 20) | ((th & kThetaMask) << 1) | (th >> 31);
+        entries[q] = pack_entry(loc, th);
     }
 }
 
@@ -265,6 +267,7 @@ int model_build(ModelTable &m) {
     m.chunk_rows = std::max(32, (((n + m.n_chunks - 1) / m.n_chunks) + 31) / 32 * 32);
     PPF_CUDA_TRY(cudaMalloc(&m.weights, std::max(1, n) * sizeof(float)));
     if (n > 0) fill_kernel<<<(n + 255) / 256, 256>>>(m.weights, n, 1.0f);
+    count_launch();
     // Every reference kernel returns early when count <= 1 (kernel.cu:406,461): a model with
     // fewer than two points has an all-zero key array, i.e. one bucket (key 0) that can never match.
     size_t total = (size_t)n * n;
@@ -292,6 +295,7 @@ int model_build(ModelTable &m) {
     int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
     model_pairs_kernel<<<grid, 256>>>(m.cloud.pos, m.cloud.nrm, m.cloud.fy, m.cloud.fz, n, m.d_dist,
                                       m.inv_d_dist, keys, theta, d_maxkd);
+    count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
 
     // sort (key, pair index): LSD radix sort, stable, so every bucket ascends in pair index
@@ -299,6 +303,7 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(cudaMalloc(&iota, total * 4));
     PPF_CUDA_TRY(cudaMalloc(&m.map, total * 4));
     iota_kernel<<<grid, 256>>>(iota, total);
+    count_launch();
     void *tmp = nullptr; size_t tmp_bytes = 0;
     PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, iota, m.map, total));
     PPF_CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
@@ -341,12 +346,14 @@ int model_build(ModelTable &m) {
     // vote payload in bucket order, per-chunk bucket slices, cell table
     PPF_CUDA_TRY(cudaMalloc(&m.entries, total * 4));
     gather_entries_kernel<<<grid, 256>>>(m.map, theta, total, n, m.chunk_rows, m.entries);
+    count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(cudaMalloc(&m.ranges, (size_t)m.U * m.n_chunks * sizeof(uint2)));
     {
         size_t t = (size_t)m.U * m.n_chunks;
         chunk_ranges_kernel<<<(int)std::min<size_t>((t + 255) / 256, 148 * 32), 256>>>(
             m.map, m.first, m.counts, m.U, n, m.chunk_rows, m.n_chunks, m.ranges);
+        count_launch();
     }
     PPF_CUDA_TRY(cudaGetLastError());
     size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
@@ -354,6 +361,7 @@ int model_build(ModelTable &m) {
     if (m.K_d > 0)
         cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256>>>(m.hashkeys, m.U, m.K_d,
                                                                                        m.d_dist, m.cell2bucket);
+        count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(cudaDeviceSynchronize());
     cudaFree(theta);

@@ -199,7 +199,9 @@ int poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r) {
     PPF_CUDA_TRY(cudaMemsetAsync(r.transformations, 0, (size_t)K * 64, 0));
     PPF_CUDA_TRY(cudaMemsetAsync(r.weighted, 0, (size_t)K * 4, 0));
     pose_kernel<<<blocks_for(K), 256>>>(r.codes, m.cloud.pos, m.cloud.nrm, scene.pos, scene.nrm, r.transformations, K);
+    count_launch();
     weight_kernel<<<blocks_for(K), 256>>>(r.codes, r.counts, m.weights, r.weighted, K);
+    count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     return PPF_OK;
 }
@@ -213,6 +215,7 @@ int cluster_run(const ModelTable &m, VoteResult &r) {
     PPF_CUDA_TRY(cudaMemsetAsync(r.scores, 0, (size_t)K * 4, 0));
     if (K <= 1) return PPF_OK;
     transquat_kernel<<<blocks_for(K), 256>>>(r.transformations, r.trans, r.rots, K);
+    count_launch();
     uint32_t *cell = nullptr, *adj = nullptr, *iota = nullptr, *shash = nullptr, *sidx = nullptr, *d_arg = nullptr;
     float3 *tin = nullptr;
     PPF_CUDA_TRY(cudaMalloc(&cell, (size_t)K * 4));
@@ -223,6 +226,7 @@ int cluster_run(const ModelTable &m, VoteResult &r) {
     PPF_CUDA_TRY(cudaMalloc(&tin, (size_t)K * sizeof(float3)));
     PPF_CUDA_TRY(cudaMalloc(&d_arg, 4));
     cellhash_kernel<<<blocks_for(K), 256>>>(r.trans, cell, adj, K, m.d_dist);
+    count_launch();
     {
         std::vector<uint32_t> h(K);
         for (int i = 0; i < K; i++) h[i] = i;
@@ -237,7 +241,9 @@ int cluster_run(const ModelTable &m, VoteResult &r) {
     PPF_CUDA_TRY(cudaMemcpyAsync(tin, r.trans, (size_t)K * sizeof(float3), cudaMemcpyDeviceToDevice, 0));
     cluster_kernel<<<blocks_for(K), 256>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
                                            m.d_dist, m.use_l1_norm, m.use_averaged_clusters);
+    count_launch();
     argmax_kernel<<<1, 1024>>>(r.scores, K, d_arg);
+    count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(cudaMemcpy(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost));
     cudaFree(tmp); cudaFree(cell); cudaFree(adj); cudaFree(iota); cudaFree(shash); cudaFree(sidx);

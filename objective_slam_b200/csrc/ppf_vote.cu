@@ -62,12 +62,53 @@ __device__ __forceinline__ FrameYZ load_frame(const float4 *__restrict__ fy, con
     return f;
 }
 
+// Voting context shared by the fast and the exact path.
+struct VoteCtx {
+    const uint32_t *map;
+    const float4 *mfy, *mfz, *mpos, *spos;
+    int nm, chunk_base, stride;
+    uint32_t *acc;
+};
+
+// Exact alpha of one vote: rebuild u and v the way trans_model_scene does (kernel.cu:330-342).
+// Taken by ~2e-4 of the votes (guard band around the 30 bin edges, degenerate u or v), so it is kept
+// out of line: the hot loop stays small enough for the instruction cache and free of divergence.
+__device__ __noinline__ void cast_vote_exact(const VoteCtx &c, const FrameYZ &FS, uint32_t s_i, uint32_t entry,
+                                             uint32_t pos) {
+    const uint32_t loc = entry & kLocMask;
+    const uint32_t pidx = __ldg(c.map + pos);
+    const int m_r = c.chunk_base + (int)loc;
+    const int m_i = (int)(pidx - (uint32_t)m_r * (uint32_t)c.nm);
+    const FrameYZ FM = load_frame(c.mfy, c.mfz, m_r);
+    const float4 mi = __ldg(c.mpos + m_i);
+    const float4 si = __ldg(c.spos + s_i);
+    float uy, uz, vy, vz;
+    frame_apply_yz(FM, mi.x, mi.y, mi.z, uy, uz);
+    frame_apply_yz(FS, si.x, si.y, si.z, vy, vz);
+    const uint32_t bin = alpha_bin_exact(uy, uz, vy, vz);
+    atomicAdd(&c.acc[bin * c.stride + loc], 1u);
+}
+
+// Fast path of one vote, branch-free.  ptxas will not predicate a shared-memory atomic (it wraps it in
+// BSSY / BRA / BSYNC, four extra issue slots per vote), so a vote that needs the exact path is not
+// skipped but redirected to a scratch counter behind the accumulator, and only sets its bit in `slow`.
+__device__ __forceinline__ void cast_vote_fast(uint32_t *acc, uint32_t stride, uint32_t scratch_idx,
+                                               uint32_t hit_theta_ones, uint32_t entry, uint32_t bit, uint32_t &slow) {
+    uint32_t bin;
+    const bool ok = alpha_bin_fast(hit_theta_ones, entry, bin);
+    const uint32_t idx = bin * stride + (entry & kLocMask);
+    atomicAdd(&acc[ok ? idx : scratch_idx], 1u);
+    if (!ok) slow |= bit;
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t *acc = reinterpret_cast<uint32_t *>(smem_raw);                       // [31][chunk_rows]
-    uint4 *queue = reinterpret_cast<uint4 *>(acc + kNAlphaBins * a.chunk_rows);   // [kHitQueue]
-    __shared__ uint32_t s_nhits, s_next, s_exact;
+    const int C = a.chunk_rows, S = acc_stride(C);
+    uint4 *queue = reinterpret_cast<uint4 *>(smem_raw);                               // [kHitQueue] hit records
+    uint32_t *cursor = reinterpret_cast<uint32_t *>(queue + kHitQueue);               // [kHitQueue] entries taken
+    uint32_t *acc = cursor + kHitQueue;                                               // [31][S] vote counters
+    __shared__ uint32_t s_nhits, s_cur, s_exact;
     __shared__ uint32_t s_red[32];
     __shared__ unsigned long long s_votes;
 
@@ -75,11 +116,10 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     const int chunk = blockIdx.x / a.ref_count;
     const int refk = blockIdx.x - chunk * a.ref_count;
     const int s_r = a.ref_start + refk * a.ref_stride;
-    const int C = a.chunk_rows;
     const int chunk_base = chunk * C;
     const uint2 *__restrict__ ranges = a.ranges + (size_t)chunk * a.U;
 
-    for (int i = tid; i < kNAlphaBins * C; i += THREADS) acc[i] = 0;
+    for (int i = tid; i < kNAlphaBins * S; i += THREADS) acc[i] = 0;
     if (tid == 0) { s_exact = 0; s_votes = 0; }
 
     // reference point (registers) and its local frame
@@ -89,11 +129,16 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
         R.x = p.x; R.y = p.y; R.z = p.z; R.nx = q.x; R.ny = q.y; R.nz = q.z; R.nn = q.w;
     }
     const FrameYZ FS = load_frame(a.sfy, a.sfz, s_r);
+    VoteCtx ctx;
+    ctx.map = a.map; ctx.mfy = a.mfy; ctx.mfz = a.mfz; ctx.mpos = a.mpos; ctx.spos = a.spos;
+    ctx.nm = a.nm; ctx.chunk_base = chunk_base; ctx.stride = S; ctx.acc = acc;
+    const uint32_t scratch_idx = (uint32_t)(kNAlphaBins * S);    // one cell behind the accumulator
     unsigned long long my_votes = 0;
     uint32_t my_exact = 0;
 
     for (int base = 0; base < a.ns; base += kHitQueue) {
-        if (tid == 0) { s_nhits = 0; s_next = 0; }
+        if (tid == 0) { s_nhits = 0; s_cur = 0; }
+        for (int i = tid; i < kHitQueue; i += THREADS) cursor[i] = 0;
         __syncthreads();
         // ---- phase 1: pairs (s_r, s_i) of this tile -> hit queue
 #pragma unroll 1
@@ -113,7 +158,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
                         if (rg.y != 0) {
                             float vy, vz;
                             frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
-                            h = make_uint4(rg.x, rg.y, theta_code(vy, vz), (uint32_t)i);
+                            h = make_uint4(rg.x, rg.y, pack_hit_theta(theta_code(vy, vz)), (uint32_t)i);
                             hit = true;
                         }
                     }
@@ -122,52 +167,74 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             const unsigned m = __ballot_sync(0xffffffffu, hit);
             if (m) {
                 uint32_t slot = 0;
-                if (lane == 0) slot = atomicAdd(&s_nhits, (uint32_t)__popc(m));
+                if (lane == 0) slot = atomicAdd(&s_nhits, (uint32_t)__popc(m));      // one atomic per warp
                 slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
                 if (hit) queue[slot] = h;
             }
         }
         __syncthreads();
-        // ---- phase 2: warps drain the queue; 32 lanes = 32 consecutive bucket entries
+        // ---- phase 2: all warps drain the queue in order, kVoteSegment entries per grab, so a
+        // 100k-entry bucket is shared by every warp instead of serialising one of them.
         const uint32_t nhits = s_nhits;
         while (true) {
-            uint32_t hi = 0;
-            if (lane == 0) hi = atomicAdd(&s_next, 1u);
+            uint32_t hi = 0, off = 0;
+            if (lane == 0) {
+                hi = *(volatile uint32_t *)&s_cur;
+                while (hi < nhits) {
+                    const uint32_t len = queue[hi].y;
+                    off = atomicAdd(&cursor[hi], (uint32_t)kVoteSegment);
+                    if (off + kVoteSegment >= len) atomicMax(&s_cur, hi + 1);        // last (or past-last) segment
+                    if (off < len) break;
+                    hi = max(hi + 1, *(volatile uint32_t *)&s_cur);
+                }
+            }
             hi = __shfl_sync(0xffffffffu, hi, 0);
             if (hi >= nhits) break;
+            off = __shfl_sync(0xffffffffu, off, 0);
             const uint4 h = queue[hi];
-            const uint32_t start = h.x, len = h.y, thv = h.z & kThetaMask, hslow = h.z >> 31;
-            if (lane == 0) my_votes += len;
-            const uint32_t *__restrict__ ent = a.entries + start;
-            for (uint32_t j0 = 0; j0 < len; j0 += 128) {
-                uint32_t e[4];
+            const uint32_t n = min((uint32_t)kVoteSegment, h.y - off);
+            const uint32_t pos0 = h.x + off;
+            const uint32_t hit_theta = (h.z & kThetaFld) | kLocMask;   // low 12 bits set: see alpha_bin_fast
+            const bool force_exact = (h.z >> 31) != 0;
+            if (lane == 0) my_votes += n;
+            const uint32_t *__restrict__ ent = a.entries + pos0;
+            if (force_exact) {
+                // degenerate scene pair (v ~ 0): every vote of this hit takes the exact path
+                for (uint32_t j = lane; j < n; j += 32) cast_vote_exact(ctx, FS, h.w, __ldg(ent + j), pos0 + j);
+                my_exact += (n + 31 - lane) / 32;
+            } else if (n == kVoteSegment) {
+                // full segment: 16 independent 128-byte warp loads in flight before the first use
+                uint32_t e[kVoteSegment / 32];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    uint32_t j = j0 + u * 32 + lane;
-                    e[u] = (j < len) ? __ldg(ent + j) : 0xFFFFFFFFu;
+                for (int u = 0; u < kVoteSegment / 32; u++) e[u] = __ldg(ent + u * 32 + lane);
+                uint32_t slow = 0;
+#pragma unroll
+                for (int u = 0; u < kVoteSegment / 32; u++) cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
+                if (slow) {
+                    my_exact += __popc(slow);
+#pragma unroll 1
+                    for (int u = 0; u < kVoteSegment / 32; u++)
+                        if ((slow >> u) & 1u) cast_vote_exact(ctx, FS, h.w, __ldg(ent + u * 32 + lane), pos0 + u * 32 + lane);
                 }
+            } else {
+                for (uint32_t j0 = 0; j0 < n; j0 += 128) {
+                    uint32_t e[4];
+                    uint32_t slow = 0;
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    uint32_t j = j0 + u * 32 + lane;
-                    if (j < len) {
-                        const uint32_t loc = e[u] >> 20;
-                        uint32_t bin;
-                        bool ok = alpha_bin_fast(thv, (e[u] >> 1) & kThetaMask, bin);
-                        if (!ok || ((e[u] & 1u) | hslow)) {
-                            // exact alpha: rebuild u and v the way trans_model_scene does
-                            const uint32_t pidx = __ldg(a.map + start + j);
-                            const int m_r = chunk_base + (int)loc;
-                            const int m_i = (int)(pidx - (uint32_t)m_r * (uint32_t)a.nm);
-                            const FrameYZ FM = load_frame(a.mfy, a.mfz, m_r);
-                            const float4 mi = __ldg(a.mpos + m_i);
-                            const float4 si = __ldg(a.spos + h.w);
-                            float uy, uz, vy, vz;
-                            frame_apply_yz(FM, mi.x, mi.y, mi.z, uy, uz);
-                            frame_apply_yz(FS, si.x, si.y, si.z, vy, vz);
-                            bin = alpha_bin_exact(uy, uz, vy, vz);
-                            my_exact++;
-                        }
-                        atomicAdd(&acc[bin * C + loc], 1u);
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t j = j0 + u * 32 + lane;
+                        e[u] = (j < n) ? __ldg(ent + j) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t j = j0 + u * 32 + lane;
+                        if (j < n) cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
+                    }
+                    if (slow) {
+                        my_exact += __popc(slow);
+#pragma unroll 1
+                        for (int u = 0; u < 4; u++)
+                            if ((slow >> u) & 1u) cast_vote_exact(ctx, FS, h.w, e[u], pos0 + j0 + u * 32 + lane);
                     }
                 }
             }
@@ -177,7 +244,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
 
     // ---- phase 3: block max, statistics, emission of candidate cells
     uint32_t lmax = 0, nz = 0;
-    for (int i = tid; i < kNAlphaBins * C; i += THREADS) {
+    for (int i = tid; i < kNAlphaBins * S; i += THREADS) {
         uint32_t c = acc[i];
         lmax = max(lmax, c);
         nz += (c != 0);
@@ -210,10 +277,10 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     const uint32_t bound = s_red[0];                       // <= final global max
     if (bound == 0) return;
     const float min_votecount = a.emit_all ? 0.0f : a.thr * (float)bound;     // model.cu:164
-    for (int i = tid; i < kNAlphaBins * C; i += THREADS) {
+    for (int i = tid; i < kNAlphaBins * S; i += THREADS) {
         uint32_t c = acc[i];
         if (c != 0 && (float)c > min_votecount) {
-            uint32_t bin = i / C, loc = i - bin * C;
+            uint32_t bin = i / S, loc = i - bin * S;
             uint32_t slot = atomicAdd(&a.scalars[0], 1u);
             if (slot < a.cand_cap) {
                 // [scene ref : 32 | model point : 26 | alpha : 6]   (kernel.cu:548-549, model.h:61-63)
@@ -304,15 +371,17 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;
         a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
         a.scalars = r.scalars; a.totals = r.votes_total;
-        const size_t smem = (size_t)kNAlphaBins * m.chunk_rows * 4 + (size_t)kHitQueue * sizeof(uint4);
+        const size_t smem = ((size_t)kNAlphaBins * acc_stride(m.chunk_rows) + 1) * 4 + (size_t)kHitQueue * (sizeof(uint4) + 4);
         const long long grid = (long long)R * m.n_chunks;
         if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, chunk) CTAs"); return PPF_ERR_UNSUPPORTED; }
         if (smem > 113 * 1024) {
             PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             vote_kernel<1024><<<(unsigned)grid, 1024, smem>>>(a);
+            count_launch();
         } else {
             PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             vote_kernel<512><<<(unsigned)grid, 512, smem>>>(a);
+            count_launch();
         }
         PPF_CUDA_TRY(cudaGetLastError());
         if (launches) (*launches)++;
@@ -366,6 +435,7 @@ int vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteRe
     filter_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256>>>(r.cand_codes, r.cand_counts, n,
                                                                          m.vote_count_threshold, global_max,
                                                                          emit_all, fc, fn, d_on);
+    count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     uint32_t K = 0;
     PPF_CUDA_TRY(cudaMemcpy(&K, d_on, 4, cudaMemcpyDeviceToHost));

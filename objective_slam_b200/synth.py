@@ -41,16 +41,19 @@ def shoemake_rotation(rng) -> np.ndarray:
 
 
 def make_model(n_points: int, seed: int = SEED_BASE, diameter: float = 100.0):
-    """Area-weighted samples of r(u) = 1 + sum_k a_k sin(f_k c_k.u + phi_k).
+    """Area-weighted samples of the star-shaped surface r(u) = 1 + sum_k a_k sin(f_k c_k.u + phi_k).
 
-    Returns (points[N,3] float32, normals[N,3] float32), points in the positive
-    octant with min coordinate 1, normals unit length and outward.
+    Ten bumps of amplitude 0.05-0.10 and angular frequency 2-7 make the normals swing far from
+    radial, so the quantised pair features spread over thousands of bins the way a real scanned
+    object's do (a near-sphere would collapse them onto a one-parameter family).
+    Returns (points[N,3] float32, normals[N,3] float32), points in the positive octant with min
+    coordinate 1, normals unit length and outward (analytic).
     """
     rng = np.random.default_rng(seed)
-    K = 6
+    K = 10
     c = _unit(rng.normal(size=(K, 3)))
-    f = rng.integers(2, 5, size=K).astype(np.float64)
-    a = rng.uniform(0.04, 0.10, size=K)
+    f = rng.integers(2, 8, size=K).astype(np.float64)
+    a = rng.uniform(0.05, 0.10, size=K)
     phi = rng.uniform(0, 2 * np.pi, size=K)
 
     def surface(u):
@@ -64,10 +67,10 @@ def make_model(n_points: int, seed: int = SEED_BASE, diameter: float = 100.0):
     pts, nrm = [], []
     need = n_points
     while need > 0:
-        u = _unit(rng.normal(size=(4 * need + 64, 3)))
+        u = _unit(rng.normal(size=(8 * need + 64, 3)))
         r, n = surface(u)
-        w = r * r / np.maximum((n * u).sum(axis=1), 0.2)     # dA / dOmega
-        keep = rng.random(len(w)) < w / (1.5 ** 2 / 0.2)
+        w = r * r / np.maximum((n * u).sum(axis=1), 0.1)     # dA / dOmega
+        keep = rng.random(len(w)) < w / (2.0 ** 2 / 0.1)
         u, r, n = u[keep][:need], r[keep][:need], n[keep][:need]
         pts.append(u * r[:, None])
         nrm.append(n)

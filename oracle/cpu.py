@@ -57,7 +57,7 @@ def lib():
                                     ctypes.POINTER(OracleResult)]
         L.oracle_result_free.argtypes = [ctypes.POINTER(OracleResult)]
         L.oracle_time_voting.restype = ctypes.c_double
-        L.oracle_time_voting.argtypes = [vp, vp, ci, vp, vp, ci, cf, cu, ci, ci, ctypes.POINTER(ctypes.c_uint64),
+        L.oracle_time_voting.argtypes = [vp, vp, ci, vp, vp, ci, cf, cu, ci, ci, ci, ctypes.POINTER(ctypes.c_uint64),
                                          ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_double)]
         _lib = L
     return _lib
@@ -124,11 +124,11 @@ def lookup(mpts, mnrm, spts, snrm, d_dist, ref_df=1, thr=0.4, use_l1_norm=False,
     return out
 
 
-def time_voting(mpts, mnrm, spts, snrm, d_dist, ref_df=1, max_refs=0, threads=0):
+def time_voting(mpts, mnrm, spts, snrm, d_dist, ref_df=1, max_refs=0, threads=0, scene_stride=1):
     """Seconds spent voting over (up to max_refs) reference points; returns dict."""
     mpts, mnrm, spts, snrm = _f32(mpts), _f32(mnrm), _f32(spts), _f32(snrm)
     pairs, votes, build_s = ctypes.c_uint64(), ctypes.c_uint64(), ctypes.c_double()
     s = lib().oracle_time_voting(_p(mpts), _p(mnrm), len(mpts), _p(spts), _p(snrm), len(spts), float(d_dist),
-                                 int(ref_df), int(max_refs), int(threads), ctypes.byref(pairs), ctypes.byref(votes),
+                                 int(ref_df), int(max_refs), int(scene_stride), int(threads), ctypes.byref(pairs), ctypes.byref(votes),
                                  ctypes.byref(build_s))
     return dict(seconds=s, pairs=pairs.value, votes=votes.value, build_seconds=build_s.value)

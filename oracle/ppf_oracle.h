@@ -57,10 +57,11 @@ int oracle_lookup(const float *mxyz, const float *mnrm, int nm, const float *sxy
                   int want_histogram, int per_vote_frames, int threads, oracle_result_t *out);
 void oracle_result_free(oracle_result_t *r);
 
-/* Timing hook for bench.py: votes cast by reference points [ref_begin, ref_end) of the ref list
- * (voting stage only, model table prebuilt inside); returns seconds, fills pairs/votes. */
+/* Timing hook for bench.py: voting stage over a bounded sample of the workload -- max_refs reference
+ * points spread over the scene, each paired with every scene_stride-th scene point (model table
+ * built inside, timed separately); returns seconds, fills pairs/votes. */
 double oracle_time_voting(const float *mxyz, const float *mnrm, int nm, const float *sxyz, const float *snrm,
-                          int ns, float d_dist, unsigned ref_df, int max_refs, int threads,
+                          int ns, float d_dist, unsigned ref_df, int max_refs, int scene_stride, int threads,
                           uint64_t *pairs, uint64_t *votes, double *build_seconds);
 
 #ifdef __cplusplus
