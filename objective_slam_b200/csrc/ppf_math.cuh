@@ -251,13 +251,13 @@ __device__ __forceinline__ void frame_apply_yz(const FrameYZ &f, float qx, float
 }
 
 // ---- alpha ------------------------------------------------------------------------
-constexpr int      kThetaBits = 19;
+constexpr int      kThetaBits = 20;
 constexpr uint32_t kThetaMask = (1u << kThetaBits) - 1u;
 constexpr uint32_t kThetaHalf = 1u << (kThetaBits - 1);
-constexpr uint32_t kAlphaGuard = 64;                  // in units of theta LSB * 30
+constexpr uint32_t kAlphaGuard = 56;                  // in units of theta LSB * 30 (error budget: DESIGN.md)
 constexpr float    kTinyUV    = 1.0e-15f;
 
-// 19-bit binary angle of (y,z) in the plane orthogonal to the normal axis.
+// 20-bit binary angle of (y,z) in the plane orthogonal to the normal axis.
 // bit 31 of the result flags vectors whose direction is numerically meaningless
 // (|u| ~ 0 or non-finite): those pairs always take the exact path.
 __device__ __forceinline__ uint32_t theta_code(float y, float z) {
@@ -281,12 +281,12 @@ __device__ __forceinline__ uint32_t alpha_bin_exact(float uy, float uz, float vy
 }
 
 // ---- packed voting payload ------------------------------------------------------------------
-// bucket entry (model pair):  [slow : 1 | theta_u : 19 | m_r - chunk_base : 12]
-// hit word     (scene pair):  [slow : 1 | (theta_v + half) mod 2^19 : 19 | 0 : 12]
-constexpr int      kLocBits   = 12;
+// bucket entry (model pair):  [slow : 1 | theta_u : 20 | m_r - chunk_base : 11]
+// hit word     (scene pair):  [slow : 1 | (theta_v + half) mod 2^20 : 20 | 0 : 11]
+constexpr int      kLocBits   = 11;
 constexpr uint32_t kLocMask   = (1u << kLocBits) - 1u;
-constexpr uint32_t kThetaFld  = kThetaMask << kLocBits;          // 0x7FFFF000
-constexpr uint32_t kGuardLo   = kAlphaGuard << (32 - kThetaBits); // guard band in units of frac << 13
+constexpr uint32_t kThetaFld  = kThetaMask << kLocBits;          // 0x7FFFF800
+constexpr uint32_t kGuardLo   = kAlphaGuard << (32 - kThetaBits); // guard band in units of frac << (32 - kThetaBits)
 
 __host__ __device__ __forceinline__ uint32_t pack_entry(uint32_t loc, uint32_t theta_code_u) {
     return (theta_code_u & 0x80000000u) | ((theta_code_u & kThetaMask) << kLocBits) | loc;
@@ -294,9 +294,9 @@ __host__ __device__ __forceinline__ uint32_t pack_entry(uint32_t loc, uint32_t t
 __host__ __device__ __forceinline__ uint32_t pack_hit_theta(uint32_t theta_code_v) {
     return (theta_code_v & 0x80000000u) | ((((theta_code_v & kThetaMask) + kThetaHalf) & kThetaMask) << kLocBits);
 }
-// Fast alpha bin: t = (theta_v - theta_u + half) mod 2^19 = (alpha + pi)/2pi * 2^19, bin = floor(30 t / 2^19).
-// With t held as t << 12, (t << 12) * 60 = (30 t) << 13: the high word is the bin, the low word the
-// fractional position inside the bin (<< 13).  `hit_theta_ones` is the hit word with its low 12 bits
+// Fast alpha bin: t = (theta_v - theta_u + half) mod 2^20 = (alpha + pi)/2pi * 2^20, bin = floor(30 t / 2^20).
+// With t held as t << 11, (t << 11) * 60 = (30 t) << 12: the high word is the bin, the low word the
+// fractional position inside the bin (<< 12).  `hit_theta_ones` is the hit word with its low 11 bits
 // set, so that subtracting the whole entry cannot borrow out of the m_r field; bit 31 (slow flag) only
 // disturbs bit 31 of the difference, which the mask drops.  Returns true when the bin is provably the
 // reference's: fraction outside the guard band around both bin edges and entry not flagged slow.

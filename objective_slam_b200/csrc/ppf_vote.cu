@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             }
         }
         __syncthreads();
-        // ---- phase 2: all warps drain the queue in order, kVoteSegment entries per grab, so a
+        // ---- phase 2: all warps drain the queue in order, kVoteGrab entries per grab, so a
         // 100k-entry bucket is shared by every warp instead of serialising one of them.
         const uint32_t nhits = s_nhits;
         while (true) {
@@ -182,8 +182,8 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
                 hi = *(volatile uint32_t *)&s_cur;
                 while (hi < nhits) {
                     const uint32_t len = queue[hi].y;
-                    off = atomicAdd(&cursor[hi], (uint32_t)kVoteSegment);
-                    if (off + kVoteSegment >= len) atomicMax(&s_cur, hi + 1);        // last (or past-last) segment
+                    off = atomicAdd(&cursor[hi], (uint32_t)kVoteGrab);
+                    if (off + kVoteGrab >= len) atomicMax(&s_cur, hi + 1);           // last (or past-last) grab
                     if (off < len) break;
                     hi = max(hi + 1, *(volatile uint32_t *)&s_cur);
                 }
@@ -192,49 +192,53 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             if (hi >= nhits) break;
             off = __shfl_sync(0xffffffffu, off, 0);
             const uint4 h = queue[hi];
-            const uint32_t n = min((uint32_t)kVoteSegment, h.y - off);
-            const uint32_t pos0 = h.x + off;
-            const uint32_t hit_theta = (h.z & kThetaFld) | kLocMask;   // low 12 bits set: see alpha_bin_fast
+            const uint32_t ngrab = min((uint32_t)kVoteGrab, h.y - off);
+            const uint32_t hit_theta = (h.z & kThetaFld) | kLocMask;   // low bits set: see alpha_bin_fast
             const bool force_exact = (h.z >> 31) != 0;
-            if (lane == 0) my_votes += n;
-            const uint32_t *__restrict__ ent = a.entries + pos0;
-            if (force_exact) {
-                // degenerate scene pair (v ~ 0): every vote of this hit takes the exact path
-                for (uint32_t j = lane; j < n; j += 32) cast_vote_exact(ctx, FS, h.w, __ldg(ent + j), pos0 + j);
-                my_exact += (n + 31 - lane) / 32;
-            } else if (n == kVoteSegment) {
-                // full segment: 16 independent 128-byte warp loads in flight before the first use
-                uint32_t e[kVoteSegment / 32];
+            if (lane == 0) my_votes += ngrab;
+            for (uint32_t o = 0; o < ngrab; o += kVoteSegment) {
+                const uint32_t n = min((uint32_t)kVoteSegment, ngrab - o);
+                const uint32_t pos0 = h.x + off + o;
+                const uint32_t *__restrict__ ent = a.entries + pos0;
+                if (force_exact) {
+                    // degenerate scene pair (v ~ 0): every vote of this hit takes the exact path
+                    for (uint32_t j = lane; j < n; j += 32) cast_vote_exact(ctx, FS, h.w, __ldg(ent + j), pos0 + j);
+                    my_exact += (n + 31 - lane) / 32;
+                } else if (n == kVoteSegment) {
+                    // full segment: 16 independent 128-byte warp loads in flight before the first use
+                    uint32_t e[kVoteSegment / 32];
 #pragma unroll
-                for (int u = 0; u < kVoteSegment / 32; u++) e[u] = __ldg(ent + u * 32 + lane);
-                uint32_t slow = 0;
-#pragma unroll
-                for (int u = 0; u < kVoteSegment / 32; u++) cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
-                if (slow) {
-                    my_exact += __popc(slow);
-#pragma unroll 1
-                    for (int u = 0; u < kVoteSegment / 32; u++)
-                        if ((slow >> u) & 1u) cast_vote_exact(ctx, FS, h.w, __ldg(ent + u * 32 + lane), pos0 + u * 32 + lane);
-                }
-            } else {
-                for (uint32_t j0 = 0; j0 < n; j0 += 128) {
-                    uint32_t e[4];
+                    for (int u = 0; u < kVoteSegment / 32; u++) e[u] = __ldg(ent + u * 32 + lane);
                     uint32_t slow = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t j = j0 + u * 32 + lane;
-                        e[u] = (j < n) ? __ldg(ent + j) : 0u;
+                    for (int u = 0; u < kVoteSegment / 32; u++)
+                        cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
+                    my_exact += __popc(slow);
+                    while (slow) {                                               // ~1e-4 of the votes
+                        const int u = __ffs(slow) - 1;
+                        slow &= slow - 1;
+                        cast_vote_exact(ctx, FS, h.w, __ldg(ent + u * 32 + lane), pos0 + u * 32 + lane);
                     }
+                } else {
+                    for (uint32_t j0 = 0; j0 < n; j0 += 128) {
+                        uint32_t e[4];
+                        uint32_t slow = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t j = j0 + u * 32 + lane;
-                        if (j < n) cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
-                    }
-                    if (slow) {
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t j = j0 + u * 32 + lane;
+                            e[u] = (j < n) ? __ldg(ent + j) : 0u;
+                        }
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            const uint32_t j = j0 + u * 32 + lane;
+                            if (j < n) cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
+                        }
                         my_exact += __popc(slow);
-#pragma unroll 1
-                        for (int u = 0; u < 4; u++)
-                            if ((slow >> u) & 1u) cast_vote_exact(ctx, FS, h.w, e[u], pos0 + j0 + u * 32 + lane);
+                        while (slow) {
+                            const int u = __ffs(slow) - 1;
+                            slow &= slow - 1;
+                            cast_vote_exact(ctx, FS, h.w, __ldg(ent + j0 + u * 32 + lane), pos0 + j0 + u * 32 + lane);
+                        }
                     }
                 }
             }
