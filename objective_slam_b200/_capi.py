@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libppf_b200.so")
+# PPF_B200_LIB selects another build of the same library (A/B timing of kernel variants)
+LIB_PATH = os.environ.get("PPF_B200_LIB") or os.path.join(_HERE, "lib", "libppf_b200.so")
 
 PPF_OK, PPF_ERR_INVALID, PPF_ERR_CUDA, PPF_ERR_UNSUPPORTED, PPF_ERR_NO_VOTES = range(5)
 PPF_MEM_HOST, PPF_MEM_DEVICE = 0, 1

@@ -10,7 +10,7 @@
 //   ModelTable hashkeys[U] counts[U] first[U] map[N*N]  -- the reference's ParallelHashArray contents
 //                                                          (parallel_hash_array.hpp:36-46) as u32
 //              entries[N*N] u32                         -- voting payload in bucket order:
-//                                                          [slow : 1 | theta_u : 20 | m_r - chunk_base : 11]
+//                                                          [theta_u : 20 | slow : 1 | m_r - chunk_base : 11]
 //              ranges[n_chunks][U] uint2                -- (start, len) of the part of bucket b whose model
 //                                                          reference points fall in chunk c (buckets ascend in
 //                                                          m_r, so every chunk is one contiguous slice)
@@ -26,10 +26,10 @@
 namespace ppf {
 
 // Shared-memory vote accumulator geometry: 31 alpha bins x chunk_rows u32 counters.
-constexpr int kMaxChunkRows = 1504;          // (31 * (1504 + 1) + 1) * 4 B = 186,624 B
+constexpr int kMaxChunkRows = 1504;          // 31 * (1504 + 1) * 4 B = 186,620 B (+ 40,960 B hit queue)
 constexpr int kHitQueue     = 2048;          // 16 B record + 4 B cursor each
-constexpr int kVoteSegment  = 512;           // bucket entries one warp votes per inner pass (16 per lane in flight)
-constexpr int kVoteGrab     = 1024;          // bucket entries one warp takes per scheduler grab
+constexpr int kVoteBatch    = 256;           // bucket entries per inner pass: 8 per lane, double-buffered in registers
+constexpr int kVoteGrab     = 2048;          // bucket entries one warp takes per scheduler grab
 // accumulator row stride: chunk_rows is a multiple of 32, so +1 makes bank = (bin + row) mod 32 --
 // lanes that hit the same model point with different alpha bins (the common case inside a bucket,
 // whose entries are sorted by m_r) fall into different banks.

@@ -281,30 +281,47 @@ __device__ __forceinline__ uint32_t alpha_bin_exact(float uy, float uz, float vy
 }
 
 // ---- packed voting payload ------------------------------------------------------------------
-// bucket entry (model pair):  [slow : 1 | theta_u : 20 | m_r - chunk_base : 11]
-// hit word     (scene pair):  [slow : 1 | (theta_v + half) mod 2^20 : 20 | 0 : 11]
+// bucket entry (model pair):  [theta_u : 20 | slow : 1 | m_r - chunk_base : 11]
+// hit word     (scene pair):  [(theta_v + half) mod 2^20 : 20 | slow : 1 | 0 : 11]
+// theta sits in the TOP bits so that a plain 32-bit subtraction wraps modulo one full turn.
 constexpr int      kLocBits   = 11;
 constexpr uint32_t kLocMask   = (1u << kLocBits) - 1u;
-constexpr uint32_t kThetaFld  = kThetaMask << kLocBits;          // 0x7FFFF800
-constexpr uint32_t kGuardLo   = kAlphaGuard << (32 - kThetaBits); // guard band in units of frac << (32 - kThetaBits)
+constexpr uint32_t kSlowBit   = 1u << kLocBits;
+constexpr int      kThetaShift = 32 - kThetaBits;                 // 12
+constexpr uint32_t kLowOnes   = (1u << kThetaShift) - 1u;         // 0xFFF
+// The subtraction below leaves junk < 2^12 under the angle, which biases the measured in-bin
+// fraction by [0, 30) guard units; the lower guard edge is widened by 30 to stay conservative.
+constexpr uint32_t kGuardLoA  = (kAlphaGuard + kNAngle) << kThetaShift;
+constexpr uint32_t kGuardLoB  = kAlphaGuard << kThetaShift;
 
 __host__ __device__ __forceinline__ uint32_t pack_entry(uint32_t loc, uint32_t theta_code_u) {
-    return (theta_code_u & 0x80000000u) | ((theta_code_u & kThetaMask) << kLocBits) | loc;
+    return ((theta_code_u & kThetaMask) << kThetaShift) | ((theta_code_u >> 31) << kLocBits) | loc;
 }
 __host__ __device__ __forceinline__ uint32_t pack_hit_theta(uint32_t theta_code_v) {
-    return (theta_code_v & 0x80000000u) | ((((theta_code_v & kThetaMask) + kThetaHalf) & kThetaMask) << kLocBits);
+    return ((((theta_code_v & kThetaMask) + kThetaHalf) & kThetaMask) << kThetaShift) | ((theta_code_v >> 31) << kLocBits);
 }
-// Fast alpha bin: t = (theta_v - theta_u + half) mod 2^20 = (alpha + pi)/2pi * 2^20, bin = floor(30 t / 2^20).
-// With t held as t << 11, (t << 11) * 60 = (30 t) << 12: the high word is the bin, the low word the
-// fractional position inside the bin (<< 12).  `hit_theta_ones` is the hit word with its low 11 bits
-// set, so that subtracting the whole entry cannot borrow out of the m_r field; bit 31 (slow flag) only
-// disturbs bit 31 of the difference, which the mask drops.  Returns true when the bin is provably the
-// reference's: fraction outside the guard band around both bin edges and entry not flagged slow.
-__device__ __forceinline__ bool alpha_bin_fast(uint32_t hit_theta_ones, uint32_t entry, uint32_t &bin) {
-    const uint32_t t12 = (hit_theta_ones - entry) & kThetaFld;
-    bin = __umulhi(t12, 2u * kNAngle);
-    const uint32_t lo = t12 * (2u * kNAngle) + kGuardLo;
-    return (lo >= 2u * kGuardLo) && ((int32_t)entry >= 0);
+// Fast alpha bin.  t = (theta_v - theta_u + half) mod 2^20 = (alpha + pi)/2pi * 2^20 and
+// bin = floor(30 t / 2^20).  `hit_ones` is the hit word with its low 12 bits set, so subtracting the
+// whole entry never borrows out of the low field and the top 20 bits of the difference are exactly t;
+// 30 * difference then has the bin in its high word and the in-bin fraction (<< 12) in its low word.
+// Returns true when the bin is provably the reference's: fraction outside the guard band around both
+// bin edges and the entry not flagged slow.
+__device__ __forceinline__ bool alpha_bin_fast(uint32_t hit_ones, uint32_t entry, uint32_t &bin) {
+    const uint32_t d = hit_ones - entry;
+    const unsigned long long p = (unsigned long long)d * (unsigned long long)kNAngle;   // one IMAD.WIDE
+    bin = (uint32_t)(p >> 32);                            // always in [0, 29]: safe to index with
+    const uint32_t lo = (uint32_t)p - kGuardLoA;
+    return (lo < (0u - kGuardLoA - kGuardLoB)) && !(entry & kSlowBit);
+}
+// Same arithmetic for the optimistic hot loop: returns the "margin" (in-bin fraction << 12, shifted
+// by the lower guard edge, modulo 2^32); the fast bin is provably right iff margin < kGuardSpan, so
+// the margins of a batch can be max-reduced and tested once.  bin is a valid index in every case.
+constexpr uint32_t kGuardSpan = 0u - kGuardLoA - kGuardLoB;
+__device__ __forceinline__ uint32_t alpha_bin_margin(uint32_t hit_ones, uint32_t entry, uint32_t &bin) {
+    const uint32_t d = hit_ones - entry;
+    const unsigned long long p = (unsigned long long)d * (unsigned long long)kNAngle;
+    bin = (uint32_t)(p >> 32);
+    return (uint32_t)p - kGuardLoA;
 }
 
 }  // namespace ppf

@@ -178,7 +178,7 @@ __global__ void iota_kernel(uint32_t *v, size_t n) {
         v[i] = (uint32_t)i;
 }
 
-// entries[q] = [slow : 1 | theta : 19 | m_r - chunk_base : 12] for sorted position q
+// entries[q] = [theta : 20 | slow : 1 | m_r - chunk_base : 11] for sorted position q
 __global__ void gather_entries_kernel(const uint32_t *__restrict__ map, const uint32_t *__restrict__ theta,
                                       size_t total, int n, int chunk_rows, uint32_t *entries) {
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {

@@ -70,11 +70,11 @@ struct VoteCtx {
     uint32_t *acc;
 };
 
-// Exact alpha of one vote: rebuild u and v the way trans_model_scene does (kernel.cu:330-342).
-// Taken by ~2e-4 of the votes (guard band around the 30 bin edges, degenerate u or v), so it is kept
-// out of line: the hot loop stays small enough for the instruction cache and free of divergence.
-__device__ __noinline__ void cast_vote_exact(const VoteCtx &c, const FrameYZ &FS, uint32_t s_i, uint32_t entry,
-                                             uint32_t pos) {
+// Exact alpha bin of one vote: rebuild u and v the way trans_model_scene does (kernel.cu:330-342).
+// Needed by ~1e-4 of the votes (guard band around the 30 bin edges, degenerate u or v); kept out of
+// line so that the hot loop stays small and free of divergence.
+__device__ __noinline__ uint32_t exact_vote_index(const VoteCtx &c, const FrameYZ &FS, uint32_t s_i, uint32_t entry,
+                                                  uint32_t pos) {
     const uint32_t loc = entry & kLocMask;
     const uint32_t pidx = __ldg(c.map + pos);
     const int m_r = c.chunk_base + (int)loc;
@@ -85,20 +85,42 @@ __device__ __noinline__ void cast_vote_exact(const VoteCtx &c, const FrameYZ &FS
     float uy, uz, vy, vz;
     frame_apply_yz(FM, mi.x, mi.y, mi.z, uy, uz);
     frame_apply_yz(FS, si.x, si.y, si.z, vy, vz);
-    const uint32_t bin = alpha_bin_exact(uy, uz, vy, vz);
-    atomicAdd(&c.acc[bin * c.stride + loc], 1u);
+    return alpha_bin_exact(uy, uz, vy, vz) * (uint32_t)c.stride + loc;
 }
 
-// Fast path of one vote, branch-free.  ptxas will not predicate a shared-memory atomic (it wraps it in
-// BSSY / BRA / BSYNC, four extra issue slots per vote), so a vote that needs the exact path is not
-// skipped but redirected to a scratch counter behind the accumulator, and only sets its bit in `slow`.
-__device__ __forceinline__ void cast_vote_fast(uint32_t *acc, uint32_t stride, uint32_t scratch_idx,
-                                               uint32_t hit_theta_ones, uint32_t entry, uint32_t bit, uint32_t &slow) {
+// The hot loop votes OPTIMISTICALLY: every entry of a batch adds 1 to the cell its fast alpha bin
+// names (always a valid cell), the guard-band margins are min-reduced and the slow flags OR-ed across
+// the batch (one VIADDMNMX and half a LOP3 per vote), and only when a batch contains a vote whose fast
+// bin is not provably the reference's (about one batch in 30) is it re-examined: such a vote is moved
+// from the optimistic cell to the exact one (-1 / +1 by the same thread, so no other thread can
+// observe a negative count, and phase 3 only reads after a barrier).  This removes the select, the
+// mask bookkeeping and all branches from the per-vote path.
+__device__ __forceinline__ void repair_vote(const VoteCtx &c, const FrameYZ &FS, uint32_t hit_ones, uint32_t s_i,
+                                            uint32_t entry, uint32_t pos, uint32_t &n_exact) {
     uint32_t bin;
-    const bool ok = alpha_bin_fast(hit_theta_ones, entry, bin);
-    const uint32_t idx = bin * stride + (entry & kLocMask);
-    atomicAdd(&acc[ok ? idx : scratch_idx], 1u);
-    if (!ok) slow |= bit;
+    if (alpha_bin_margin(hit_ones, entry, bin) >= kGuardSpan || (entry & kSlowBit)) {
+        atomicSub(&c.acc[bin * (uint32_t)c.stride + (entry & kLocMask)], 1u);
+        atomicAdd(&c.acc[exact_vote_index(c, FS, s_i, entry, pos)], 1u);
+        n_exact++;
+    }
+}
+
+// One full batch: E entries per lane, entry u of this lane sits at table position pos_lane + 32 u.
+template <int E>
+__device__ __forceinline__ void vote_batch(const VoteCtx &c, const FrameYZ &FS, uint32_t hit_ones, uint32_t s_i,
+                                           const uint32_t (&e)[E], uint32_t pos_lane, uint32_t &n_exact) {
+    uint32_t worst = 0, flags = 0;
+#pragma unroll
+    for (int u = 0; u < E; u++) {
+        uint32_t bin;
+        worst = max(worst, alpha_bin_margin(hit_ones, e[u], bin));
+        flags |= e[u];
+        atomicAdd(&c.acc[bin * (uint32_t)c.stride + (e[u] & kLocMask)], 1u);
+    }
+    if (worst >= kGuardSpan || (flags & kSlowBit)) {
+#pragma unroll
+        for (int u = 0; u < E; u++) repair_vote(c, FS, hit_ones, s_i, e[u], pos_lane + 32 * u, n_exact);
+    }
 }
 
 template <int THREADS>
@@ -132,7 +154,6 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     VoteCtx ctx;
     ctx.map = a.map; ctx.mfy = a.mfy; ctx.mfz = a.mfz; ctx.mpos = a.mpos; ctx.spos = a.spos;
     ctx.nm = a.nm; ctx.chunk_base = chunk_base; ctx.stride = S; ctx.acc = acc;
-    const uint32_t scratch_idx = (uint32_t)(kNAlphaBins * S);    // one cell behind the accumulator
     unsigned long long my_votes = 0;
     uint32_t my_exact = 0;
 
@@ -193,51 +214,68 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             off = __shfl_sync(0xffffffffu, off, 0);
             const uint4 h = queue[hi];
             const uint32_t ngrab = min((uint32_t)kVoteGrab, h.y - off);
-            const uint32_t hit_theta = (h.z & kThetaFld) | kLocMask;   // low bits set: see alpha_bin_fast
-            const bool force_exact = (h.z >> 31) != 0;
+            const uint32_t hit_theta = h.z | kLowOnes;                 // low 12 bits set: see alpha_bin_fast
+            const bool force_exact = (h.z & kSlowBit) != 0;
             if (lane == 0) my_votes += ngrab;
-            for (uint32_t o = 0; o < ngrab; o += kVoteSegment) {
-                const uint32_t n = min((uint32_t)kVoteSegment, ngrab - o);
-                const uint32_t pos0 = h.x + off + o;
-                const uint32_t *__restrict__ ent = a.entries + pos0;
-                if (force_exact) {
-                    // degenerate scene pair (v ~ 0): every vote of this hit takes the exact path
-                    for (uint32_t j = lane; j < n; j += 32) cast_vote_exact(ctx, FS, h.w, __ldg(ent + j), pos0 + j);
-                    my_exact += (n + 31 - lane) / 32;
-                } else if (n == kVoteSegment) {
-                    // full segment: 16 independent 128-byte warp loads in flight before the first use
-                    uint32_t e[kVoteSegment / 32];
+            const uint32_t pos_grab = h.x + off;
+            const uint32_t *__restrict__ ent = a.entries + pos_grab;
+            if (force_exact) {
+                // degenerate scene pair (v ~ 0): every vote of this hit takes the exact path
+                for (uint32_t j = lane; j < ngrab; j += 32) {
+                    atomicAdd(&acc[exact_vote_index(ctx, FS, h.w, __ldg(ent + j), pos_grab + j)], 1u);
+                    my_exact++;
+                }
+                continue;
+            }
+            // Full batches, software-pipelined: the 8 loads of batch b+1 are in flight while batch b votes.
+            constexpr int E = kVoteBatch / 32;
+            const uint32_t nfull = ngrab / kVoteBatch;
+            uint32_t e0[E], e1[E];
+            if (nfull) {
 #pragma unroll
-                    for (int u = 0; u < kVoteSegment / 32; u++) e[u] = __ldg(ent + u * 32 + lane);
-                    uint32_t slow = 0;
+                for (int u = 0; u < E; u++) e0[u] = __ldg(ent + u * 32 + lane);
+            }
+            for (uint32_t bi = 0; bi < nfull; bi += 2) {
+                if (bi + 1 < nfull) {
 #pragma unroll
-                    for (int u = 0; u < kVoteSegment / 32; u++)
-                        cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
-                    my_exact += __popc(slow);
-                    while (slow) {                                               // ~1e-4 of the votes
-                        const int u = __ffs(slow) - 1;
-                        slow &= slow - 1;
-                        cast_vote_exact(ctx, FS, h.w, __ldg(ent + u * 32 + lane), pos0 + u * 32 + lane);
+                    for (int u = 0; u < E; u++) e1[u] = __ldg(ent + (bi + 1) * kVoteBatch + u * 32 + lane);
+                }
+                vote_batch<E>(ctx, FS, hit_theta, h.w, e0, pos_grab + bi * kVoteBatch + lane, my_exact);
+                if (bi + 1 < nfull) {
+                    if (bi + 2 < nfull) {
+#pragma unroll
+                        for (int u = 0; u < E; u++) e0[u] = __ldg(ent + (bi + 2) * kVoteBatch + u * 32 + lane);
                     }
-                } else {
-                    for (uint32_t j0 = 0; j0 < n; j0 += 128) {
-                        uint32_t e[4];
-                        uint32_t slow = 0;
+                    vote_batch<E>(ctx, FS, hit_theta, h.w, e1, pos_grab + (bi + 1) * kVoteBatch + lane, my_exact);
+                }
+            }
+            // tail of the hit: fewer than kVoteBatch entries
+            const uint32_t done = nfull * kVoteBatch;
+            if (done < ngrab) {
+                const uint32_t n = ngrab - done;
+                for (uint32_t j0 = 0; j0 < n; j0 += 128) {
+                    uint32_t e[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t j = j0 + u * 32 + lane;
+                        e[u] = (j < n) ? __ldg(ent + done + j) : 0u;
+                    }
+                    uint32_t worst = 0, flags = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t j = j0 + u * 32 + lane;
+                        if (j < n) {
+                            uint32_t bin;
+                            worst = max(worst, alpha_bin_margin(hit_theta, e[u], bin));
+                            flags |= e[u];
+                            atomicAdd(&acc[bin * (uint32_t)S + (e[u] & kLocMask)], 1u);
+                        }
+                    }
+                    if (worst >= kGuardSpan || (flags & kSlowBit)) {
 #pragma unroll
                         for (int u = 0; u < 4; u++) {
                             const uint32_t j = j0 + u * 32 + lane;
-                            e[u] = (j < n) ? __ldg(ent + j) : 0u;
-                        }
-#pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const uint32_t j = j0 + u * 32 + lane;
-                            if (j < n) cast_vote_fast(acc, (uint32_t)S, scratch_idx, hit_theta, e[u], 1u << u, slow);
-                        }
-                        my_exact += __popc(slow);
-                        while (slow) {
-                            const int u = __ffs(slow) - 1;
-                            slow &= slow - 1;
-                            cast_vote_exact(ctx, FS, h.w, __ldg(ent + j0 + u * 32 + lane), pos0 + j0 + u * 32 + lane);
+                            if (j < n) repair_vote(ctx, FS, hit_theta, h.w, e[u], pos_grab + done + j, my_exact);
                         }
                     }
                 }
@@ -375,7 +413,7 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;
         a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
         a.scalars = r.scalars; a.totals = r.votes_total;
-        const size_t smem = ((size_t)kNAlphaBins * acc_stride(m.chunk_rows) + 1) * 4 + (size_t)kHitQueue * (sizeof(uint4) + 4);
+        const size_t smem = (size_t)kNAlphaBins * acc_stride(m.chunk_rows) * 4 + (size_t)kHitQueue * (sizeof(uint4) + 4);
         const long long grid = (long long)R * m.n_chunks;
         if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, chunk) CTAs"); return PPF_ERR_UNSUPPORTED; }
         if (smem > 113 * 1024) {
