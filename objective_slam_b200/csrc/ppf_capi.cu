@@ -189,13 +189,14 @@ int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const 
     PPF_CHECK_ARG(lk && (K == 0 || (codes_dev && counts_dev)), "set_survivors: NULL argument");
     unsigned long long *c = nullptr; uint32_t *n = nullptr;
     if (K) {
-        PPF_CUDA_TRY(cudaMalloc(&c, K * 8));
-        PPF_CUDA_TRY(cudaMalloc(&n, K * 4));
-        PPF_CUDA_TRY(cudaMemcpy(c, codes_dev, K * 8, cudaMemcpyDeviceToDevice));
-        PPF_CUDA_TRY(cudaMemcpy(n, counts_dev, K * 4, cudaMemcpyDeviceToDevice));
+        int rc0 = lk->res.ws.reserve(K * 12 + order_survivors_bytes(K));
+        if (rc0) return rc0;
+        c = lk->res.ws.take<unsigned long long>(K);
+        n = lk->res.ws.take<uint32_t>(K);
+        PPF_CUDA_TRY(cudaMemcpyAsync(c, codes_dev, K * 8, cudaMemcpyDeviceToDevice, 0));
+        PPF_CUDA_TRY(cudaMemcpyAsync(n, counts_dev, K * 4, cudaMemcpyDeviceToDevice, 0));
     }
     int rc = order_survivors(lk->res, K, c, n);
-    cudaFree(c); cudaFree(n);
     lk->stats.num_top_votes = (uint32_t)lk->res.K;
     return rc;
 }

@@ -56,7 +56,20 @@ struct ModelTable {
     int use_l1_norm = 0, use_averaged_clusters = 0;
 };
 
+// Grow-only device scratch arena: the per-lookup temporaries (filter output, sort buffers, CUB
+// temp storage, clustering tables) are carved out of it, so a lookup performs no cudaMalloc /
+// cudaFree in steady state (both synchronise the device and cost up to 100s of ms under load).
+struct Workspace {
+    char *base = nullptr;
+    size_t cap = 0, used = 0;
+    int reserve(size_t bytes);                 // make room for `bytes` (+ alignment slack), reset the bump pointer
+    void *take_bytes(size_t bytes);            // 256-byte aligned slice, nullptr if the reservation was too small
+    template <typename T> T *take(size_t n) { return static_cast<T *>(take_bytes(n * sizeof(T))); }
+    void release();
+};
+
 struct VoteResult {                           // device buffers of one ppf_lookup
+    Workspace ws;
     // candidates emitted by the vote kernel (superset of the survivors)
     unsigned long long *cand_codes = nullptr;
     uint32_t *cand_counts = nullptr;
@@ -104,6 +117,7 @@ int  vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ra
               int emit_all, VoteResult &r, unsigned long long *pairs_out, int *launches);
 int  vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteResult &r);
 int  order_survivors(VoteResult &r, size_t K, unsigned long long *codes_in, uint32_t *counts_in);
+size_t order_survivors_bytes(size_t K);
 int  vote_reserve_K(VoteResult &r, size_t K);
 void vote_result_free(VoteResult &r);
 int  poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r);

@@ -122,6 +122,11 @@ __global__ void cellhash_kernel(const float3 *trans, uint32_t *cell_hash, uint32
 
 // rot_clustering_kernel (kernel.cu:702-763). sorted_hash/sorted_idx: poses ordered by
 // (cell hash, pose index) -- the ParallelHashArray of model.cu:222-223.
+// One WARP per pose: the 32 lanes test 32 neighbour poses at a time (quaternion distance,
+// translation distance), then the accepted weights are added to the score one by one in lane order,
+// i.e. in exactly the order the reference's single thread visits them (neighbour cell 0..26, then
+// ascending pose index inside the cell) -- float addition is not associative once a score passes
+// 2^24, so the order is part of the result.
 __global__ void cluster_kernel(const float3 *trans_in, const float4 *quats, const float *weights,
                                const uint32_t *adj_hash, const uint32_t *sorted_hash, const uint32_t *sorted_idx,
                                float *scores, float3 *trans_out, int count, float trans_thresh, int use_l1_norm,
@@ -129,44 +134,64 @@ __global__ void cluster_kernel(const float3 *trans_in, const float4 *quats, cons
     if (count <= 1) return;
     const float rot_thresh = 2 * d_angle0();                                  // ROT_THRESH, kernel.h:17
     const float rot_thresh_sq = rot_thresh * rot_thresh;
-    for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
-        float3 tt = trans_in[idx];
-        float4 q = quats[idx];
+    const int lane = threadIdx.x & 31;
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < count; idx += warps) {
+        const float3 tt = trans_in[idx];
+        const float4 q = quats[idx];
         float score = 1;
         float3 to = tt;
         for (int ab = 0; ab < 27; ab++) {
-            uint32_t h = adj_hash[27 * (size_t)idx + ab];
+            const uint32_t h = adj_hash[27 * (size_t)idx + ab];
             if (h == 0) continue;
             int lo = 0, hi = count;                                           // lower_bound over the cell hashes
             while (lo < hi) {
                 int mid = (lo + hi) >> 1;
                 if (sorted_hash[mid] < h) lo = mid + 1; else hi = mid;
             }
-            for (int p = lo; p < count && sorted_hash[p] == h; p++) {
-                uint32_t j = sorted_idx[p];
-                float w = weights[j];
-                float4 qj = quats[j];
-                float qd = fabsf(__fmul_rn(8.0f, __fsub_rn(1.0f, dot4(q.x, q.y, q.z, q.w, qj.x, qj.y, qj.z, qj.w))));
-                if (qd < rot_thresh_sq) {
-                    float3 tj = trans_in[j];
-                    if (!use_l1_norm) {
-                        float nd = norm3(__fsub_rn(tt.x, tj.x), __fsub_rn(tt.y, tj.y), __fsub_rn(tt.z, tj.z));
-                        if (!(nd < trans_thresh)) continue;
+            for (int base = lo; base < count; base += 32) {
+                const int p = base + lane;
+                const bool valid = p < count && sorted_hash[p] == h;
+                const unsigned run = __ballot_sync(0xffffffffu, valid);
+                if (!run) break;
+                bool pass = false;
+                float w = 0.f;
+                float3 tj = make_float3(0.f, 0.f, 0.f);
+                if (valid) {
+                    const uint32_t j = sorted_idx[p];
+                    w = weights[j];
+                    const float4 qj = quats[j];
+                    const float qd = fabsf(__fmul_rn(8.0f, __fsub_rn(1.0f, dot4(q.x, q.y, q.z, q.w, qj.x, qj.y, qj.z, qj.w))));
+                    if (qd < rot_thresh_sq) {
+                        tj = trans_in[j];
+                        pass = true;
+                        if (!use_l1_norm) {
+                            const float nd = norm3(__fsub_rn(tt.x, tj.x), __fsub_rn(tt.y, tj.y), __fsub_rn(tt.z, tj.z));
+                            pass = nd < trans_thresh;
+                        }
                     }
+                }
+                unsigned acc = __ballot_sync(0xffffffffu, pass);
+                while (acc) {                                                 // sequential, reference order
+                    const int src = __ffs(acc) - 1;
+                    acc &= acc - 1;
+                    const float wj = __shfl_sync(0xffffffffu, w, src);
                     if (use_averaged_clusters) {                              // kernel.cu:747-752
+                        const float tx = __shfl_sync(0xffffffffu, tj.x, src), ty = __shfl_sync(0xffffffffu, tj.y, src),
+                                    tz = __shfl_sync(0xffffffffu, tj.z, src);
                         to.x = __fmul_rn(score, to.x); to.y = __fmul_rn(score, to.y); to.z = __fmul_rn(score, to.z);
-                        to.x = __fadd_rn(to.x, __fmul_rn(w, tj.x));
-                        to.y = __fadd_rn(to.y, __fmul_rn(w, tj.y));
-                        to.z = __fadd_rn(to.z, __fmul_rn(w, tj.z));
-                        float inv = div_full_ftz(1.0f, __fadd_rn(score, w));
+                        to.x = __fadd_rn(to.x, __fmul_rn(wj, tx));
+                        to.y = __fadd_rn(to.y, __fmul_rn(wj, ty));
+                        to.z = __fadd_rn(to.z, __fmul_rn(wj, tz));
+                        const float inv = div_full_ftz(1.0f, __fadd_rn(score, wj));
                         to.x = __fmul_rn(inv, to.x); to.y = __fmul_rn(inv, to.y); to.z = __fmul_rn(inv, to.z);
                     }
-                    score = __fadd_rn(score, w);
+                    score = __fadd_rn(score, wj);
                 }
+                if (run != 0xffffffffu) break;                                // the run of equal hashes ended here
             }
         }
-        scores[idx] = score;
-        trans_out[idx] = to;
+        if (lane == 0) { scores[idx] = score; trans_out[idx] = to; }
     }
 }
 
@@ -189,6 +214,10 @@ __global__ void argmax_kernel(const float *scores, int count, uint32_t *out) {
         __syncthreads();
     }
     if (threadIdx.x == 0) *out = (count > 0 && si[0] != 0x7FFFFFFF) ? (uint32_t)si[0] : 0u;
+}
+
+__global__ void iota_u32_kernel(uint32_t *v, int n) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = (uint32_t)i;
 }
 
 static int blocks_for(size_t count) { return (int)std::min<size_t>(std::max<size_t>((count + 255) / 256, 1), 1024); }
@@ -216,38 +245,35 @@ int cluster_run(const ModelTable &m, VoteResult &r) {
     if (K <= 1) return PPF_OK;
     transquat_kernel<<<blocks_for(K), 256>>>(r.transformations, r.trans, r.rots, K);
     count_launch();
-    uint32_t *cell = nullptr, *adj = nullptr, *iota = nullptr, *shash = nullptr, *sidx = nullptr, *d_arg = nullptr;
-    float3 *tin = nullptr;
-    PPF_CUDA_TRY(cudaMalloc(&cell, (size_t)K * 4));
-    PPF_CUDA_TRY(cudaMalloc(&adj, (size_t)K * 27 * 4));
-    PPF_CUDA_TRY(cudaMalloc(&iota, (size_t)K * 4));
-    PPF_CUDA_TRY(cudaMalloc(&shash, (size_t)K * 4));
-    PPF_CUDA_TRY(cudaMalloc(&sidx, (size_t)K * 4));
-    PPF_CUDA_TRY(cudaMalloc(&tin, (size_t)K * sizeof(float3)));
-    PPF_CUDA_TRY(cudaMalloc(&d_arg, 4));
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, K);
+    int rc = r.ws.reserve((size_t)K * (4 + 27 * 4 + 4 + 4 + 4 + sizeof(float3)) + 4 + tb);
+    if (rc) return rc;
+    uint32_t *cell = r.ws.take<uint32_t>(K), *adj = r.ws.take<uint32_t>((size_t)K * 27);
+    uint32_t *iota = r.ws.take<uint32_t>(K), *shash = r.ws.take<uint32_t>(K), *sidx = r.ws.take<uint32_t>(K);
+    float3 *tin = r.ws.take<float3>(K);
+    uint32_t *d_arg = r.ws.take<uint32_t>(1);
+    void *tmp = r.ws.take_bytes(tb);
+    if (!cell || !adj || !iota || !shash || !sidx || !tin || !d_arg || !tmp) {
+        set_last_error("cluster: workspace too small");
+        return PPF_ERR_CUDA;
+    }
     cellhash_kernel<<<blocks_for(K), 256>>>(r.trans, cell, adj, K, m.d_dist);
     count_launch();
-    {
-        std::vector<uint32_t> h(K);
-        for (int i = 0; i < K; i++) h[i] = i;
-        PPF_CUDA_TRY(cudaMemcpy(iota, h.data(), (size_t)K * 4, cudaMemcpyHostToDevice));
-    }
-    void *tmp = nullptr; size_t tb = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, tb, cell, shash, iota, sidx, K);
-    PPF_CUDA_TRY(cudaMalloc(&tmp, tb));
+    iota_u32_kernel<<<blocks_for(K), 256>>>(iota, K);
+    count_launch();
     PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, cell, shash, iota, sidx, K));
     // rot_clustering_kernel updates translations in place while neighbours read them (a race in the
     // reference when use_averaged_clusters is set); we read a snapshot instead, which is deterministic.
     PPF_CUDA_TRY(cudaMemcpyAsync(tin, r.trans, (size_t)K * sizeof(float3), cudaMemcpyDeviceToDevice, 0));
-    cluster_kernel<<<blocks_for(K), 256>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
+    cluster_kernel<<<(int)std::min<size_t>(((size_t)K * 32 + 255) / 256, 148 * 64), 256>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
                                            m.d_dist, m.use_l1_norm, m.use_averaged_clusters);
     count_launch();
     argmax_kernel<<<1, 1024>>>(r.scores, K, d_arg);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(cudaMemcpy(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost));
-    cudaFree(tmp); cudaFree(cell); cudaFree(adj); cudaFree(iota); cudaFree(shash); cudaFree(sidx);
-    cudaFree(tin); cudaFree(d_arg);
     return PPF_OK;
 }
 

@@ -349,6 +349,25 @@ __global__ void filter_kernel(const unsigned long long *codes, const uint32_t *c
     }
 }
 
+int Workspace::reserve(size_t bytes) {
+    bytes += 16 * 256;                                     // alignment slack for up to 16 slices
+    used = 0;
+    if (bytes <= cap) return PPF_OK;
+    if (base) cudaFree(base);
+    base = nullptr; cap = 0;
+    size_t want = bytes + bytes / 2;
+    if (cudaMalloc(&base, want) != cudaSuccess) { set_last_error("workspace: out of device memory"); return PPF_ERR_CUDA; }
+    cap = want;
+    return PPF_OK;
+}
+void *Workspace::take_bytes(size_t bytes) {
+    size_t off = (used + 255) & ~(size_t)255;
+    if (off + bytes > cap) return nullptr;
+    used = off + bytes;
+    return base + off;
+}
+void Workspace::release() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+
 static int ensure(void **p, size_t bytes) {
     if (*p) cudaFree(*p);
     *p = nullptr;
@@ -359,6 +378,7 @@ void vote_result_free(VoteResult &r) {
     cudaFree(r.cand_codes); cudaFree(r.cand_counts); cudaFree(r.scalars); cudaFree(r.votes_total);
     cudaFree(r.codes); cudaFree(r.counts); cudaFree(r.transformations); cudaFree(r.weighted);
     cudaFree(r.trans); cudaFree(r.rots); cudaFree(r.scores);
+    r.ws.release();
     r = VoteResult();
 }
 
@@ -444,21 +464,30 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
 // Threshold against the global maximum and order (count desc, code asc): the order that
 // thrust::sort + histogram + sort_by_key(greater<float>) leaves (model.cu:148-158; the
 // comparator sort is a stable merge sort, so equal counts stay in ascending code order).
+// Workspace bytes order_survivors needs for K survivors (sort buffers + CUB temp storage).
+size_t order_survivors_bytes(size_t K) {
+    size_t tb = 0, tb2 = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, tb, (unsigned long long *)nullptr, (unsigned long long *)nullptr,
+                                    (uint32_t *)nullptr, (uint32_t *)nullptr, K);
+    cub::DeviceRadixSort::SortPairsDescending(nullptr, tb2, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                              (unsigned long long *)nullptr, (unsigned long long *)nullptr, K);
+    return K * 12 + std::max(tb, tb2) + 1024;
+}
+
+// codes_in / counts_in may live in r.ws (taken before the call); the scratch comes from r.ws too.
 int order_survivors(VoteResult &r, size_t K, unsigned long long *codes_in, uint32_t *counts_in) {
     if (K == 0) { r.K = 0; return PPF_OK; }
     int rc = vote_reserve_K(r, K);
     if (rc) return rc;
-    unsigned long long *c1 = nullptr; uint32_t *n1 = nullptr;
-    PPF_CUDA_TRY(cudaMalloc(&c1, K * 8));
-    PPF_CUDA_TRY(cudaMalloc(&n1, K * 4));
-    void *tmp = nullptr; size_t tb = 0, tb2 = 0;
+    size_t tb = 0, tb2 = 0;
+    unsigned long long *c1 = r.ws.take<unsigned long long>(K);
+    uint32_t *n1 = r.ws.take<uint32_t>(K);
     cub::DeviceRadixSort::SortPairs(nullptr, tb, codes_in, c1, counts_in, n1, K);
     cub::DeviceRadixSort::SortPairsDescending(nullptr, tb2, n1, r.counts, c1, r.codes, K);
-    PPF_CUDA_TRY(cudaMalloc(&tmp, std::max(tb, tb2)));
+    void *tmp = r.ws.take_bytes(std::max(tb, tb2));
+    if (!c1 || !n1 || !tmp) { set_last_error("order_survivors: workspace too small"); return PPF_ERR_CUDA; }
     PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, codes_in, c1, counts_in, n1, K));
     PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tb2, n1, r.counts, c1, r.codes, K));
-    PPF_CUDA_TRY(cudaDeviceSynchronize());
-    cudaFree(tmp); cudaFree(c1); cudaFree(n1);
     r.K = K;
     return PPF_OK;
 }
@@ -469,11 +498,12 @@ int vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteRe
     uint32_t n = h[0];
     r.K = 0;
     if (n == 0 || global_max == 0) return PPF_OK;
-    unsigned long long *fc = nullptr; uint32_t *fn = nullptr, *d_on = nullptr;
-    PPF_CUDA_TRY(cudaMalloc(&fc, (size_t)n * 8));
-    PPF_CUDA_TRY(cudaMalloc(&fn, (size_t)n * 4));
-    PPF_CUDA_TRY(cudaMalloc(&d_on, 4));
-    PPF_CUDA_TRY(cudaMemset(d_on, 0, 4));
+    int rc = r.ws.reserve((size_t)n * 12 + 256 + order_survivors_bytes(n));
+    if (rc) return rc;
+    unsigned long long *fc = r.ws.take<unsigned long long>(n);
+    uint32_t *fn = r.ws.take<uint32_t>(n);
+    uint32_t *d_on = r.ws.take<uint32_t>(1);
+    PPF_CUDA_TRY(cudaMemsetAsync(d_on, 0, 4, 0));
     filter_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256>>>(r.cand_codes, r.cand_counts, n,
                                                                          m.vote_count_threshold, global_max,
                                                                          emit_all, fc, fn, d_on);
@@ -481,9 +511,7 @@ int vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteRe
     PPF_CUDA_TRY(cudaGetLastError());
     uint32_t K = 0;
     PPF_CUDA_TRY(cudaMemcpy(&K, d_on, 4, cudaMemcpyDeviceToHost));
-    int rc = order_survivors(r, K, fc, fn);
-    cudaFree(fc); cudaFree(fn); cudaFree(d_on);
-    return rc;
+    return order_survivors(r, K, fc, fn);
 }
 
 }  // namespace ppf
