@@ -81,7 +81,7 @@ class Scene:
         return ppf, keys
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and C is not None and getattr(C, "lib", None) is not None:
             C.lib.ppf_scene_destroy(self._h)
             self._h = None
 
@@ -147,7 +147,7 @@ class Lookup:
                             st.num_exact_alpha, st.ms_vote, st.ms_finalize, st.ms_pose_cluster, status)
 
     def close(self):
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and C is not None and getattr(C, "lib", None) is not None:
             C.lib.ppf_lookup_destroy(self._h)
             self._h = None
 
@@ -222,7 +222,7 @@ class Model:
         if self._lookup is not None:
             self._lookup.close()
             self._lookup = None
-        if getattr(self, "_h", None):
+        if getattr(self, "_h", None) and C is not None and getattr(C, "lib", None) is not None:
             C.lib.ppf_model_destroy(self._h)
             self._h = None
 

@@ -286,12 +286,29 @@ int model_build(ModelTable &m) {
         return PPF_OK;
     }
 
-    uint32_t *keys = nullptr, *keys_sorted = nullptr, *theta = nullptr, *iota = nullptr, *d_U = nullptr;
-    int *d_maxkd = nullptr;
-    PPF_CUDA_TRY(cudaMalloc(&keys, total * 4));
-    PPF_CUDA_TRY(cudaMalloc(&theta, total * 4));
-    PPF_CUDA_TRY(cudaMalloc(&d_maxkd, 4));
-    PPF_CUDA_TRY(cudaMemset(d_maxkd, 0xFF, 4));
+    // All build temporaries live in ONE scratch allocation (one cudaMalloc + one cudaFree per build:
+    // allocator calls, not kernels, dominate the build time of a small model).
+    size_t sort_tmp = 0, rle_tmp = 0, scan_tmp = 0;
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                 (uint32_t *)nullptr, (uint32_t *)nullptr, total));
+    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, rle_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                    (uint32_t *)nullptr, (uint32_t *)nullptr, total));
+    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, total));
+    const size_t cub_tmp = std::max(sort_tmp, std::max(rle_tmp, scan_tmp));
+    Workspace ws;
+    int rc = ws.reserve(4 * total * 4 + cub_tmp + 64);
+    if (rc) return rc;
+    uint32_t *keys = ws.take<uint32_t>(total), *theta = ws.take<uint32_t>(total);
+    uint32_t *keys_sorted = ws.take<uint32_t>(total), *iota = ws.take<uint32_t>(total);
+    uint32_t *d_U = ws.take<uint32_t>(1);
+    int *d_maxkd = ws.take<int>(1);
+    void *tmp = ws.take_bytes(cub_tmp);
+    struct Release { Workspace &w; ~Release() { w.release(); } } release_on_exit{ws};
+    if (!keys || !theta || !keys_sorted || !iota || !d_U || !d_maxkd || !tmp) {
+        set_last_error("model: scratch arena too small");
+        return PPF_ERR_CUDA;
+    }
+    PPF_CUDA_TRY(cudaMemsetAsync(d_maxkd, 0xFF, 4, 0));
     int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
     model_pairs_kernel<<<grid, 256>>>(m.cloud.pos, m.cloud.nrm, m.cloud.fy, m.cloud.fz, n, m.d_dist,
                                       m.inv_d_dist, keys, theta, d_maxkd);
@@ -299,49 +316,29 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(cudaGetLastError());
 
     // sort (key, pair index): LSD radix sort, stable, so every bucket ascends in pair index
-    PPF_CUDA_TRY(cudaMalloc(&keys_sorted, total * 4));
-    PPF_CUDA_TRY(cudaMalloc(&iota, total * 4));
     PPF_CUDA_TRY(cudaMalloc(&m.map, total * 4));
     iota_kernel<<<grid, 256>>>(iota, total);
     count_launch();
-    void *tmp = nullptr; size_t tmp_bytes = 0;
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys, keys_sorted, iota, m.map, total));
-    PPF_CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys, keys_sorted, iota, m.map, total));
-    cudaFree(tmp); tmp = nullptr;
-    cudaFree(iota); cudaFree(keys);
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, keys, keys_sorted, iota, m.map, total));
 
-    // run-length encode -> unique keys + counts (histogram(), util.hpp:30-52); scan -> first index
-    uint32_t *uk = nullptr, *uc = nullptr;
-    PPF_CUDA_TRY(cudaMalloc(&uk, total * 4));
-    PPF_CUDA_TRY(cudaMalloc(&uc, total * 4));
-    PPF_CUDA_TRY(cudaMalloc(&d_U, 4));
-    tmp_bytes = 0;
-    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, keys_sorted, uk, uc, d_U, total));
-    PPF_CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, keys_sorted, uk, uc, d_U, total));
-    cudaFree(tmp); tmp = nullptr;
+    // run-length encode -> unique keys + counts (histogram(), util.hpp:30-52); scan -> first index.
+    // keys / iota are dead after the sort and are reused as the RLE outputs.
+    uint32_t *uk = keys, *uc = iota;
+    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, rle_tmp, keys_sorted, uk, uc, d_U, total));
     int h_maxkd = -1;
     PPF_CUDA_TRY(cudaMemcpy(&m.U, d_U, 4, cudaMemcpyDeviceToHost));
     PPF_CUDA_TRY(cudaMemcpy(&h_maxkd, d_maxkd, 4, cudaMemcpyDeviceToHost));
-    cudaFree(d_U); cudaFree(d_maxkd); cudaFree(keys_sorted);
     if (h_maxkd >= 65536) {
-        cudaFree(uk); cudaFree(uc); cudaFree(theta);
         set_last_error("model: d_dist is more than 65536x smaller than the model extent");
         return PPF_ERR_UNSUPPORTED;
     }
     m.K_d = h_maxkd + 1;
-    PPF_CUDA_TRY(cudaMalloc(&m.hashkeys, m.U * 4));
-    PPF_CUDA_TRY(cudaMalloc(&m.counts, m.U * 4));
-    PPF_CUDA_TRY(cudaMalloc(&m.first, m.U * 4));
-    PPF_CUDA_TRY(cudaMemcpy(m.hashkeys, uk, m.U * 4, cudaMemcpyDeviceToDevice));
-    PPF_CUDA_TRY(cudaMemcpy(m.counts, uc, m.U * 4, cudaMemcpyDeviceToDevice));
-    cudaFree(uk); cudaFree(uc);
-    tmp_bytes = 0;
-    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, m.counts, m.first, m.U));
-    PPF_CUDA_TRY(cudaMalloc(&tmp, tmp_bytes));
-    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, tmp_bytes, m.counts, m.first, m.U));
-    cudaFree(tmp); tmp = nullptr;
+    PPF_CUDA_TRY(cudaMalloc(&m.hashkeys, (size_t)m.U * 4));
+    PPF_CUDA_TRY(cudaMalloc(&m.counts, (size_t)m.U * 4));
+    PPF_CUDA_TRY(cudaMalloc(&m.first, (size_t)m.U * 4));
+    PPF_CUDA_TRY(cudaMemcpyAsync(m.hashkeys, uk, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, 0));
+    PPF_CUDA_TRY(cudaMemcpyAsync(m.counts, uc, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, 0));
+    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, m.counts, m.first, m.U));
 
     // vote payload in bucket order, per-chunk bucket slices, cell table
     PPF_CUDA_TRY(cudaMalloc(&m.entries, total * 4));
@@ -358,13 +355,13 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(cudaGetLastError());
     size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
     PPF_CUDA_TRY(cudaMalloc(&m.cell2bucket, ncell * 4));
-    if (m.K_d > 0)
+    if (m.K_d > 0) {
         cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256>>>(m.hashkeys, m.U, m.K_d,
                                                                                        m.d_dist, m.cell2bucket);
         count_launch();
+    }
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(cudaDeviceSynchronize());
-    cudaFree(theta);
     return PPF_OK;
 }
 
