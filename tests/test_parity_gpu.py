@@ -161,3 +161,15 @@ def test_device_resident_clouds_match_host_clouds():
     t = lambda x: torch.from_numpy(x).cuda()
     b = ppf.Model(t(mp), t(mn), d).ppf_lookup(ppf.Scene(t(sp), t(sn), d, 2))
     assert (a.votes == b.votes).all() and (a.voteCounts == b.voteCounts).all() and (bits(a.pose) == bits(b.pose)).all()
+
+
+def test_config3_model_build_stress_5k():
+    """BASELINE configs[2]: 5k-point model = 25 M pairs, sort-based table vs the reference's ParallelHashArray."""
+    import objective_slam_b200 as ppf
+    from oracle import refgpu
+    mp, mn, _, _, d, _ = clouds(5000, 10, 0.05, seed=55)
+    rt = refgpu.RefModel(mp, mn, d).table()
+    t = ppf.Model(mp, mn, d).table()
+    for name, a, b in zip(("hashkeys", "counts", "first", "map"), rt, t):
+        assert a.shape == b.shape and (a == b).all(), name
+    assert len(t[3]) == 25_000_000 and t[1][0] == 5000          # bucket 0 = the self pairs

@@ -102,3 +102,42 @@ def test_cpu_clustering_variant_agrees_with_gpu_clustering():
         dt, ang = _ht_dist(r.pose.astype(np.float64), T)
         assert dt < 10.0 and ang < np.radians(12)
     assert abs(np.linalg.det(b.pose[:3, :3].astype(np.float64)) - 1) < 1e-4
+
+
+def test_config4_multi_model_database():
+    """BASELINE configs[3] (reduced): several models with different d_dist against one scene through
+    ppf_registration; each pose must equal the object-level lookup of that (scene, model) pair."""
+    import objective_slam_b200 as ppf
+    from objective_slam_b200 import synth
+    models, dd = [], []
+    for k in range(4):
+        mp, mn = synth.make_model(600 + 100 * k, seed=900 + k)
+        models.append((mp, mn)); dd.append(synth.d_dist_for(mp, 0.05 + 0.01 * k))
+    sp, sn, T = synth.make_scene(models[1][0], models[1][1], 20000, seed=77)
+    poses, status = ppf.ppf_registration([(sp, sn)], models, dd, ref_point_downsample_factor=10)
+    for j, ((mp, mn), d) in enumerate(zip(models, dd)):
+        r = ppf.Model(mp, mn, d).ppf_lookup(ppf.Scene(sp, sn, d, 10), arrays=False)
+        assert status[0, j] == r.status
+        assert (poses[0, j].view(np.uint32) == r.pose.view(np.uint32)).all()
+    dt, ang = _ht_dist(poses[0, 1].astype(np.float64), T)       # the planted model is found
+    assert dt < 10.0 and ang < np.radians(12)
+
+
+def test_config5_dense_million_point_scene():
+    """BASELINE configs[4] (reference points subsampled): a 1M-point TSDF-like lattice cloud.  The reference
+    overflows int at 46,341 points; here pair counts are 64-bit and nothing of size N_s^2 exists."""
+    import objective_slam_b200 as ppf
+    from objective_slam_b200 import synth, _capi as C
+    sp, sn = synth.make_lattice_scene(1_000_000, pitch=0.5)
+    mp, mn = synth.make_lattice_scene(2000, pitch=0.5, seed=3)
+    d = synth.d_dist_for(mp)
+    m, s = ppf.Model(mp, mn, d), ppf.Scene(sp, sn, d, 20000)
+    whole = m.ppf_lookup(s, arrays=True)
+    assert whole.num_scene_pairs == 50 * 1_000_000 and whole.num_nonunique_votes > 0
+    lk = ppf.Lookup()
+    votes = 0
+    for r in range(2):
+        C.check(C.lib.ppf_lookup_vote(m._h, s._h, 20000, r, 2, lk._h))
+        votes += lk.stats().num_nonunique_votes
+    assert votes == whole.num_nonunique_votes
+    assert (whole.votes >> np.uint64(32)).max() < 1_000_000
