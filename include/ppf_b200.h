@@ -96,6 +96,21 @@ int ppf_model_table_get(const ppf_model_t *model, uint32_t *hashkeys, size_t *co
 int ppf_model_features(const ppf_model_t *model, int ref_begin, int ref_end, int other_begin,
                        int other_end, float *ppfs_out, uint32_t *keys_out);
 
+/* ---- Operator-level entry points (the MATLAB prototype's function names) ---------- */
+/* point_pair_feature + my_discretize for n independent pairs (matlab/point_pair_feature.m:1-11,
+ * my_discretize.m:3-4; compute_ppf + disc_feature, kernel.cu:94-122).  p1,n1,p2,n2: n x 3 host floats.
+ * raw_out (n x 4, may be NULL) = F = (|d|, ang(n1,d), ang(n2,d), ang(n1,n2)); disc_out (n x 4, may be NULL) =
+ * F - mod(F, step) with step d_dist for F1 and 2*pi/30 for F2..F4; keys_out (n, may be NULL) = the 32-bit
+ * hash the table is keyed on. */
+int ppf_point_pair_feature(const float *p1, const float *n1, const float *p2, const float *n2, size_t n,
+                           float d_dist, float *raw_out, float *disc_out, uint32_t *keys_out);
+/* trans_model_scene (matlab/trans_model_scene.m:1-41, kernel.cu:302-349) for n independent tuples (all
+ * n x 3 host floats): T_m_g and T_s_g (n x 16 row-major each, may be NULL), alpha in radians (n, may be NULL)
+ * and the accumulator bin alpha_idx in [0,30] (n, may be NULL). */
+int ppf_trans_model_scene(const float *m_r, const float *n_r_m, const float *m_i, const float *s_r,
+                          const float *n_r_s, const float *s_i, size_t n, float *T_m_g, float *T_s_g,
+                          float *alpha, uint32_t *alpha_idx);
+
 /* ---- Lookup (voting -> poses -> clustering) ------------------------------------- */
 typedef struct ppf_lookup_stats {
     uint64_t num_scene_pairs;       /* R * N_s pairs processed by this call (the metric's unit)   */

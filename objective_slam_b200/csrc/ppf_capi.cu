@@ -118,6 +118,16 @@ int ppf_model_features(const ppf_model_t *m, int rb, int re, int ob, int oe, flo
     return features_tile(m->table.cloud, m->table.d_dist, 1, rb, re, ob, oe, ppfs_out, keys_out);
 }
 
+// ---- operator-level entry points -----------------------------------------------------
+int ppf_point_pair_feature(const float *p1, const float *n1, const float *p2, const float *n2, size_t n, float d_dist,
+                           float *raw_out, float *disc_out, uint32_t *keys_out) {
+    return op_point_pair_feature(p1, n1, p2, n2, n, d_dist, raw_out, disc_out, keys_out);
+}
+int ppf_trans_model_scene(const float *m_r, const float *n_r_m, const float *m_i, const float *s_r, const float *n_r_s,
+                          const float *s_i, size_t n, float *T_m_g, float *T_s_g, float *alpha, uint32_t *alpha_idx) {
+    return op_trans_model_scene(m_r, n_r_m, m_i, s_r, n_r_s, s_i, n, T_m_g, T_s_g, alpha, alpha_idx);
+}
+
 // ---- Lookup -----------------------------------------------------------------------
 int ppf_lookup_create(ppf_lookup_t **out) {
     PPF_CHECK_ARG(out, "lookup: out is NULL");

@@ -220,6 +220,100 @@ __global__ void iota_u32_kernel(uint32_t *v, int n) {
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) v[i] = (uint32_t)i;
 }
 
+// ---- operator-level kernels (MATLAB function names) ------------------------------------------------
+__global__ void pair_feature_kernel(const float *p1, const float *n1, const float *p2, const float *n2, size_t n,
+                                    float d_dist, float4 *raw, float4 *disc, uint32_t *keys) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        PointN a, b;
+        a.x = p1[3 * i]; a.y = p1[3 * i + 1]; a.z = p1[3 * i + 2];
+        a.nx = n1[3 * i]; a.ny = n1[3 * i + 1]; a.nz = n1[3 * i + 2]; a.nn = norm3(a.nx, a.ny, a.nz);
+        b.x = p2[3 * i]; b.y = p2[3 * i + 1]; b.z = p2[3 * i + 2];
+        b.nx = n2[3 * i]; b.ny = n2[3 * i + 1]; b.nz = n2[3 * i + 2]; b.nn = norm3(b.nx, b.ny, b.nz);
+        if (raw) {                                                      // compute_ppf, kernel.cu:109-122
+            float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
+            float nd = norm3(dx, dy, dz);
+            raw[i] = make_float4(nd, acosf(div_full_ftz(dot3(a.nx, a.ny, a.nz, dx, dy, dz), __fmul_rn(nd, a.nn))),
+                                 acosf(div_full_ftz(dot3(b.nx, b.ny, b.nz, dx, dy, dz), __fmul_rn(nd, b.nn))),
+                                 acosf(div_full_ftz(dot3(a.nx, a.ny, a.nz, b.nx, b.ny, b.nz), __fmul_rn(a.nn, b.nn))));
+        }
+        FeatureBins fb = pair_feature_bins(a, b, d_dist, 1.0f / d_dist);
+        float4 q;
+        if (fb.kd < 0) q.x = CUDART_NAN_F;
+        else if (fb.kd == 0x7FFFFFFF) q.x = __fsub_rn(fb.f1, fmodf(fb.f1, d_dist));
+        else q.x = quant_value(fb.kd, d_dist);
+        q.y = __uint_as_float(angle_bits(fb.k1)); q.z = __uint_as_float(angle_bits(fb.k2)); q.w = __uint_as_float(angle_bits(fb.k3));
+        if (disc) disc[i] = q;
+        if (keys) keys[i] = (q.x != q.x) ? 0u : fnv1a_4(__float_as_uint(q.x), __float_as_uint(q.y), __float_as_uint(q.z), __float_as_uint(q.w));
+    }
+}
+
+__global__ void trans_model_scene_kernel(const float *m_r, const float *n_r_m, const float *m_i, const float *s_r,
+                                         const float *n_r_s, const float *s_i, size_t n, float *Tmg, float *Tsg,
+                                         float *alpha, uint32_t *alpha_idx) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float ry, rz;
+        Mat4 A, B;
+        frame_angles(n_r_m[3 * i], n_r_m[3 * i + 1], n_r_m[3 * i + 2], ry, rz);
+        frame_from_angles(m_r[3 * i], m_r[3 * i + 1], m_r[3 * i + 2], ry, rz, A);
+        frame_angles(n_r_s[3 * i], n_r_s[3 * i + 1], n_r_s[3 * i + 2], ry, rz);
+        frame_from_angles(s_r[3 * i], s_r[3 * i + 1], s_r[3 * i + 2], ry, rz, B);
+        float uy = mat4_row_apply(A.m[1], m_i[3 * i], m_i[3 * i + 1], m_i[3 * i + 2]);
+        float uz = mat4_row_apply(A.m[2], m_i[3 * i], m_i[3 * i + 1], m_i[3 * i + 2]);
+        float vy = mat4_row_apply(B.m[1], s_i[3 * i], s_i[3 * i + 1], s_i[3 * i + 2]);
+        float vz = mat4_row_apply(B.m[2], s_i[3 * i], s_i[3 * i + 1], s_i[3 * i + 2]);
+        if (Tmg) for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) Tmg[16 * i + 4 * r + c] = A.m[r][c];
+        if (Tsg) for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) Tsg[16 * i + 4 * r + c] = B.m[r][c];
+        if (alpha) alpha[i] = atan2f(__fmaf_rn(uy, vz, -__fmul_rn(uz, vy)), __fmaf_rn(uz, vz, __fmaf_rn(uy, vy, 0.0f)));
+        if (alpha_idx) alpha_idx[i] = alpha_bin_exact(uy, uz, vy, vz);
+    }
+}
+
+// host arrays in, host arrays out (debug / operator-level API; not a hot path)
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    int up(const void *h, size_t bytes) {
+        if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) return PPF_ERR_CUDA;
+        if (h && bytes && cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return PPF_ERR_CUDA;
+        return PPF_OK;
+    }
+    int down(void *h, size_t bytes) { return (h && bytes && cudaMemcpy(h, p, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) ? PPF_ERR_CUDA : PPF_OK; }
+};
+
+int op_point_pair_feature(const float *p1, const float *n1, const float *p2, const float *n2, size_t n, float d_dist,
+                          float *raw_out, float *disc_out, uint32_t *keys_out) {
+    if (!p1 || !n1 || !p2 || !n2 || !(d_dist > 0.f)) { set_last_error("point_pair_feature: NULL input or d_dist <= 0"); return PPF_ERR_INVALID; }
+    if (n == 0) return PPF_OK;
+    DevBuf a, b, c, d, r, q, k;
+    if (a.up(p1, n * 12) || b.up(n1, n * 12) || c.up(p2, n * 12) || d.up(n2, n * 12) || r.up(nullptr, n * 16) ||
+        q.up(nullptr, n * 16) || k.up(nullptr, n * 4)) { set_last_error("point_pair_feature: device allocation/copy failed"); return PPF_ERR_CUDA; }
+    pair_feature_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(
+        (const float *)a.p, (const float *)b.p, (const float *)c.p, (const float *)d.p, n, d_dist,
+        raw_out ? (float4 *)r.p : nullptr, disc_out ? (float4 *)q.p : nullptr, keys_out ? (uint32_t *)k.p : nullptr);
+    count_launch();
+    PPF_CUDA_TRY(cudaGetLastError());
+    if (r.down(raw_out, n * 16) || q.down(disc_out, n * 16) || k.down(keys_out, n * 4)) { set_last_error("point_pair_feature: copy back failed"); return PPF_ERR_CUDA; }
+    return PPF_OK;
+}
+
+int op_trans_model_scene(const float *m_r, const float *n_r_m, const float *m_i, const float *s_r, const float *n_r_s,
+                         const float *s_i, size_t n, float *T_m_g, float *T_s_g, float *alpha, uint32_t *alpha_idx) {
+    if (!m_r || !n_r_m || !m_i || !s_r || !n_r_s || !s_i) { set_last_error("trans_model_scene: NULL input"); return PPF_ERR_INVALID; }
+    if (n == 0) return PPF_OK;
+    DevBuf in[6], tm, ts, al, ai;
+    const float *src[6] = {m_r, n_r_m, m_i, s_r, n_r_s, s_i};
+    for (int i = 0; i < 6; i++) if (in[i].up(src[i], n * 12)) { set_last_error("trans_model_scene: upload failed"); return PPF_ERR_CUDA; }
+    if (tm.up(nullptr, n * 64) || ts.up(nullptr, n * 64) || al.up(nullptr, n * 4) || ai.up(nullptr, n * 4)) { set_last_error("trans_model_scene: allocation failed"); return PPF_ERR_CUDA; }
+    trans_model_scene_kernel<<<(int)std::min<size_t>((n + 127) / 128, 148 * 8), 128>>>(
+        (const float *)in[0].p, (const float *)in[1].p, (const float *)in[2].p, (const float *)in[3].p, (const float *)in[4].p,
+        (const float *)in[5].p, n, T_m_g ? (float *)tm.p : nullptr, T_s_g ? (float *)ts.p : nullptr,
+        alpha ? (float *)al.p : nullptr, alpha_idx ? (uint32_t *)ai.p : nullptr);
+    count_launch();
+    PPF_CUDA_TRY(cudaGetLastError());
+    if (tm.down(T_m_g, n * 64) || ts.down(T_s_g, n * 64) || al.down(alpha, n * 4) || ai.down(alpha_idx, n * 4)) { set_last_error("trans_model_scene: copy back failed"); return PPF_ERR_CUDA; }
+    return PPF_OK;
+}
+
 static int blocks_for(size_t count) { return (int)std::min<size_t>(std::max<size_t>((count + 255) / 256, 1), 1024); }
 
 int poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r) {
