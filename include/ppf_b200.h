@@ -96,6 +96,14 @@ int ppf_model_table_get(const ppf_model_t *model, uint32_t *hashkeys, size_t *co
 int ppf_model_features(const ppf_model_t *model, int ref_begin, int ref_end, int other_begin,
                        int other_end, float *ppfs_out, uint32_t *keys_out);
 
+/* ---- Pre-processing: voxel-grid downsample (the caller right before the hot path) ---- */
+/* voxelGridDownsample (alignment.cpp:79-87) = pcl::VoxelGrid<PointNormal> with a cubic leaf: one output point
+ * per occupied leaf, in ascending leaf order, = centroid of the positions AND of the (un-normalised) normals
+ * of the points in it.  out_xyz / out_nrm: dense n_out x 3 arrays with room for n points, in the memory
+ * space `mem` names (like the inputs). */
+int ppf_voxel_grid(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem, float leaf,
+                   float *out_xyz, float *out_nrm, int *n_out);
+
 /* ---- Operator-level entry points (the MATLAB prototype's function names) ---------- */
 /* point_pair_feature + my_discretize for n independent pairs (matlab/point_pair_feature.m:1-11,
  * my_discretize.m:3-4; compute_ppf + disc_feature, kernel.cu:94-122).  p1,n1,p2,n2: n x 3 host floats.

@@ -2,6 +2,6 @@
 
 Importing the package loads lib/libppf_b200.so and fails loudly if it is missing (no CPU fallback).
 """
-from . import synth  # noqa: F401
+from . import io, operators, synth, voxel  # noqa: F401
 from .api import Lookup, LookupResult, Model, Scene, ppf_registration  # noqa: F401
 from ._capi import PpfError  # noqa: F401

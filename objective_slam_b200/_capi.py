@@ -20,7 +20,7 @@ EXPORTS = [
     "ppf_last_error", "ppf_version", "ppf_kernel_launch_count",
     "ppf_scene_create", "ppf_scene_destroy", "ppf_scene_num_points", "ppf_scene_features",
     "ppf_model_create", "ppf_model_destroy", "ppf_model_num_points", "ppf_model_table_sizes",
-    "ppf_model_table_get", "ppf_model_features", "ppf_point_pair_feature", "ppf_trans_model_scene",
+    "ppf_model_table_get", "ppf_model_features", "ppf_point_pair_feature", "ppf_trans_model_scene", "ppf_voxel_grid",
     "ppf_lookup_create", "ppf_lookup_destroy", "ppf_model_lookup", "ppf_lookup_vote",
     "ppf_lookup_local_max", "ppf_lookup_finalize", "ppf_lookup_survivors", "ppf_lookup_set_survivors",
     "ppf_lookup_copy_survivors",
@@ -82,6 +82,7 @@ def _load():
     L.ppf_model_table_sizes.argtypes = [vp, P(sz), P(sz)]
     L.ppf_model_table_get.argtypes = [vp, vp, vp, vp, vp]
     L.ppf_model_features.argtypes = [vp, ci, ci, ci, ci, vp, vp]
+    L.ppf_voxel_grid.argtypes = [vp, ci, vp, ci, ci, ci, cf, vp, vp, P(ci)]
     L.ppf_point_pair_feature.argtypes = [vp, vp, vp, vp, sz, cf, vp, vp, vp]
     L.ppf_trans_model_scene.argtypes = [vp, vp, vp, vp, vp, vp, sz, vp, vp, vp, vp]
     L.ppf_lookup_create.argtypes = [P(vp)]

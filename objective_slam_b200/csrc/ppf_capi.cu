@@ -118,6 +118,12 @@ int ppf_model_features(const ppf_model_t *m, int rb, int re, int ob, int oe, flo
     return features_tile(m->table.cloud, m->table.d_dist, 1, rb, re, ob, oe, ppfs_out, keys_out);
 }
 
+// ---- pre-processing --------------------------------------------------------------------
+int ppf_voxel_grid(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem, float leaf,
+                   float *out_xyz, float *out_nrm, int *n_out) {
+    return voxel_grid_run(xyz, xyz_stride, nrm, nrm_stride, n, mem, leaf, out_xyz, out_nrm, n_out);
+}
+
 // ---- operator-level entry points -----------------------------------------------------
 int ppf_point_pair_feature(const float *p1, const float *n1, const float *p2, const float *n2, size_t n, float d_dist,
                            float *raw_out, float *disc_out, uint32_t *keys_out) {

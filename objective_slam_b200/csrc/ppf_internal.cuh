@@ -122,6 +122,8 @@ int  vote_reserve_K(VoteResult &r, size_t K);
 void vote_result_free(VoteResult &r);
 int  poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r);
 int  cluster_run(const ModelTable &m, VoteResult &r);
+int  voxel_grid_run(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, float leaf, float *out_xyz,
+                    float *out_nrm, int *n_out);
 int  op_point_pair_feature(const float *p1, const float *n1, const float *p2, const float *n2, size_t n, float d_dist,
                            float *raw_out, float *disc_out, uint32_t *keys_out);
 int  op_trans_model_scene(const float *m_r, const float *n_r_m, const float *m_i, const float *s_r, const float *n_r_s,
