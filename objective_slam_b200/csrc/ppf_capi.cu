@@ -61,7 +61,7 @@ int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm
     PPF_CHECK_ARG(out, "scene: out is NULL");
     *out = nullptr;
     ppf_scene *s = new ppf_scene();
-    int rc = cloud_create(xyz, xyz_stride, nrm, nrm_stride, n, mem, s->cloud);
+    int rc = cloud_create(xyz, xyz_stride, nrm, nrm_stride, n, mem, s->cloud, /*spatial_sort=*/true);
     if (rc) { cloud_free(s->cloud); delete s; return rc; }
     *out = s;
     return PPF_OK;

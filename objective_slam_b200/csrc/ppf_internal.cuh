@@ -38,6 +38,13 @@ __host__ __device__ constexpr int acc_stride(int chunk_rows) { return chunk_rows
 struct Cloud {
     int n = 0;
     float4 *pos = nullptr, *nrm = nullptr, *fy = nullptr, *fz = nullptr;
+    // Scene clouds are stored in Morton (Z-curve) order so that 32 consecutive points are spatially
+    // compact: the vote kernel culls whole warps / tiles of scene points that lie farther from the
+    // reference point than any model pair is long.  order[p] = caller's index of stored point p,
+    // inv[i] = stored position of the caller's point i (nullptr for model clouds: identity).
+    uint32_t *order = nullptr, *inv = nullptr;
+    float4 *gbox_lo = nullptr, *gbox_hi = nullptr;     // AABB of every 32-point group
+    float4 *tbox_lo = nullptr, *tbox_hi = nullptr;     // AABB of every kHitQueue-point tile
 };
 
 struct ModelTable {
@@ -106,7 +113,7 @@ void set_last_error(const std::string &msg);
 void count_launch(int n = 1);
 
 // ---- entry points of the translation units -------------------------------------------
-int  cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, Cloud &c);
+int  cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, Cloud &c, bool spatial_sort = false);
 void cloud_free(Cloud &c);
 int  features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int ob, int oe,
                    float *ppfs_host, uint32_t *keys_host);

@@ -22,25 +22,84 @@ namespace ppf {
 // ---------------------------------------------------------------------------------
 // Cloud
 // ---------------------------------------------------------------------------------
+// Stored point p = the caller's point order[p] (identity when order == nullptr).
 __global__ void pack_cloud_kernel(const float *__restrict__ xyz, int xs, const float *__restrict__ nrm,
-                                  int ns, int n, float4 *pos, float4 *nrmo, float4 *fy, float4 *fz) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float px = xyz[(size_t)i * xs], py = xyz[(size_t)i * xs + 1], pz = xyz[(size_t)i * xs + 2];
-    float nx = nrm[(size_t)i * ns], ny = nrm[(size_t)i * ns + 1], nz = nrm[(size_t)i * ns + 2];
-    pos[i] = make_float4(px, py, pz, 0.f);
-    nrmo[i] = make_float4(nx, ny, nz, norm3(nx, ny, nz));
+                                  int ns, int n, const uint32_t *__restrict__ order, float4 *pos, float4 *nrmo,
+                                  float4 *fy, float4 *fz) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    size_t i = order ? order[p] : (uint32_t)p;
+    float px = xyz[i * xs], py = xyz[i * xs + 1], pz = xyz[i * xs + 2];
+    float nx = nrm[i * ns], ny = nrm[i * ns + 1], nz = nrm[i * ns + 2];
+    pos[p] = make_float4(px, py, pz, 0.f);
+    nrmo[p] = make_float4(nx, ny, nz, norm3(nx, ny, nz));
     FrameYZ f = frame_yz(px, py, pz, nx, ny, nz);
-    fy[i] = make_float4(f.y[0], f.y[1], f.y[2], f.y[3]);
-    fz[i] = make_float4(f.z[0], f.z[1], f.z[2], f.z[3]);
+    fy[p] = make_float4(f.y[0], f.y[1], f.y[2], f.y[3]);
+    fz[p] = make_float4(f.z[0], f.z[1], f.z[2], f.z[3]);
 }
 
 void cloud_free(Cloud &c) {
     cudaFree(c.pos); cudaFree(c.nrm); cudaFree(c.fy); cudaFree(c.fz);
+    cudaFree(c.order); cudaFree(c.inv); cudaFree(c.gbox_lo); cudaFree(c.gbox_hi); cudaFree(c.tbox_lo); cudaFree(c.tbox_hi);
     c = Cloud();
 }
 
-int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, Cloud &c) {
+// ---- spatial (Morton) order + bounding boxes of a scene cloud --------------------------------------
+__device__ __forceinline__ void atomic_min_f(float *addr, float v) {
+    if (v >= 0) atomicMin((int *)addr, __float_as_int(v)); else atomicMax((unsigned int *)addr, __float_as_uint(v));
+}
+__device__ __forceinline__ void atomic_max_f(float *addr, float v) {
+    if (v >= 0) atomicMax((int *)addr, __float_as_int(v)); else atomicMin((unsigned int *)addr, __float_as_uint(v));
+}
+__global__ void bbox_kernel(const float *xyz, int xs, int n, float *mm) {
+    float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        for (int c = 0; c < 3; c++) {
+            float v = xyz[(size_t)i * xs + c];
+            if (fabsf(v) < 3.0e38f) { lo[c] = fminf(lo[c], v); hi[c] = fmaxf(hi[c], v); }
+        }
+    for (int c = 0; c < 3; c++) {
+        for (int o = 16; o; o >>= 1) {
+            lo[c] = fminf(lo[c], __shfl_xor_sync(0xffffffffu, lo[c], o));
+            hi[c] = fmaxf(hi[c], __shfl_xor_sync(0xffffffffu, hi[c], o));
+        }
+        if ((threadIdx.x & 31) == 0) { atomic_min_f(mm + c, lo[c]); atomic_max_f(mm + 3 + c, hi[c]); }
+    }
+}
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {               // 10 bits -> every third bit
+    v = (v | (v << 16)) & 0x030000FFu; v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;  v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__global__ void morton_kernel(const float *xyz, int xs, int n, const float *mm, uint32_t *key, uint32_t *idx) {
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t k = 0;
+        for (int c = 0; c < 3; c++) {
+            float lo = mm[c], ext = mm[3 + c] - mm[c];
+            float t = ext > 0.f ? (xyz[(size_t)i * xs + c] - lo) / ext : 0.f;
+            int q = (t == t) ? min(1023, max(0, (int)(t * 1024.f))) : 1023;    // NaN / Inf points go last
+            k |= spread10((uint32_t)q) << c;
+        }
+        key[i] = k; idx[i] = (uint32_t)i;
+    }
+}
+__global__ void invert_kernel(const uint32_t *order, int n, uint32_t *inv) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) inv[order[p]] = (uint32_t)p;
+}
+// AABB of every `group` consecutive stored points (NaN coordinates are ignored by fminf / fmaxf).
+__global__ void boxes_kernel(const float4 *pos, int n, int group, float4 *lo_out, float4 *hi_out, int n_boxes) {
+    for (int b = blockIdx.x * blockDim.x + threadIdx.x; b < n_boxes; b += gridDim.x * blockDim.x) {
+        float3 lo = make_float3(3.0e38f, 3.0e38f, 3.0e38f), hi = make_float3(-3.0e38f, -3.0e38f, -3.0e38f);
+        for (int i = b * group; i < min(n, (b + 1) * group); i++) {
+            float4 p = pos[i];
+            lo.x = fminf(lo.x, p.x); lo.y = fminf(lo.y, p.y); lo.z = fminf(lo.z, p.z);
+            hi.x = fmaxf(hi.x, p.x); hi.y = fmaxf(hi.y, p.y); hi.z = fmaxf(hi.z, p.z);
+        }
+        lo_out[b] = make_float4(lo.x, lo.y, lo.z, 0.f); hi_out[b] = make_float4(hi.x, hi.y, hi.z, 0.f);
+    }
+}
+
+int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, Cloud &c, bool spatial_sort) {
     if (!xyz || !nrm || n < 0 || xs < 3 || ns < 3) {
         set_last_error("cloud: null pointer, negative size or stride < 3");
         return PPF_ERR_INVALID;
@@ -52,20 +111,54 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
     PPF_CUDA_TRY(cudaMalloc(&c.fy, nn * sizeof(float4)));
     PPF_CUDA_TRY(cudaMalloc(&c.fz, nn * sizeof(float4)));
     if (n == 0) return PPF_OK;
+    Workspace ws;
+    struct Release { Workspace &w; ~Release() { w.release(); } } rel{ws};
+    size_t bx = ((size_t)(n - 1) * xs + 3) * sizeof(float), bn = ((size_t)(n - 1) * ns + 3) * sizeof(float);
+    size_t sort_tmp = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                    (uint32_t *)nullptr, n);
+    int rc = ws.reserve((mem == PPF_MEM_HOST ? bx + bn : 0) + (spatial_sort ? (size_t)n * 12 + sort_tmp + 64 : 0) + 64);
+    if (rc) return rc;
     const float *dx = xyz, *dn = nrm;
-    float *tmpx = nullptr, *tmpn = nullptr;
     if (mem == PPF_MEM_HOST) {
-        size_t bx = ((size_t)(n - 1) * xs + 3) * sizeof(float), bn = ((size_t)(n - 1) * ns + 3) * sizeof(float);
-        PPF_CUDA_TRY(cudaMalloc(&tmpx, bx));
-        PPF_CUDA_TRY(cudaMalloc(&tmpn, bn));
-        PPF_CUDA_TRY(cudaMemcpyAsync(tmpx, xyz, bx, cudaMemcpyHostToDevice, 0));
-        PPF_CUDA_TRY(cudaMemcpyAsync(tmpn, nrm, bn, cudaMemcpyHostToDevice, 0));
-        dx = tmpx; dn = tmpn;
+        float *tx = (float *)ws.take_bytes(bx), *tn = (float *)ws.take_bytes(bn);
+        PPF_CUDA_TRY(cudaMemcpyAsync(tx, xyz, bx, cudaMemcpyHostToDevice, 0));
+        PPF_CUDA_TRY(cudaMemcpyAsync(tn, nrm, bn, cudaMemcpyHostToDevice, 0));
+        dx = tx; dn = tn;
     }
-    pack_cloud_kernel<<<(n + 255) / 256, 256>>>(dx, xs, dn, ns, n, c.pos, c.nrm, c.fy, c.fz);
+    const int grid = std::min((n + 255) / 256, 148 * 8);
+    if (spatial_sort) {
+        float *mm = ws.take<float>(6);
+        uint32_t *key = ws.take<uint32_t>(n), *key_s = ws.take<uint32_t>(n), *idx = ws.take<uint32_t>(n);
+        void *tmp = ws.take_bytes(sort_tmp);
+        PPF_CUDA_TRY(cudaMalloc(&c.order, (size_t)n * 4));
+        PPF_CUDA_TRY(cudaMalloc(&c.inv, (size_t)n * 4));
+        const float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+        PPF_CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, 0));
+        bbox_kernel<<<grid, 256>>>(dx, xs, n, mm);
+        count_launch();
+        morton_kernel<<<grid, 256>>>(dx, xs, n, mm, key, idx);
+        count_launch();
+        PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, key, key_s, idx, c.order, n, 0, 30));
+        invert_kernel<<<grid, 256>>>(c.order, n, c.inv);
+        count_launch();
+    }
+    pack_cloud_kernel<<<(n + 255) / 256, 256>>>(dx, xs, dn, ns, n, c.order, c.pos, c.nrm, c.fy, c.fz);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
-    if (tmpx) { PPF_CUDA_TRY(cudaStreamSynchronize(0)); cudaFree(tmpx); cudaFree(tmpn); }
+    if (spatial_sort) {
+        const int ng = (n + 31) / 32, nt = (n + kHitQueue - 1) / kHitQueue;
+        PPF_CUDA_TRY(cudaMalloc(&c.gbox_lo, (size_t)ng * sizeof(float4)));
+        PPF_CUDA_TRY(cudaMalloc(&c.gbox_hi, (size_t)ng * sizeof(float4)));
+        PPF_CUDA_TRY(cudaMalloc(&c.tbox_lo, (size_t)nt * sizeof(float4)));
+        PPF_CUDA_TRY(cudaMalloc(&c.tbox_hi, (size_t)nt * sizeof(float4)));
+        boxes_kernel<<<std::min((ng + 127) / 128, 148 * 8), 128>>>(c.pos, n, 32, c.gbox_lo, c.gbox_hi, ng);
+        count_launch();
+        boxes_kernel<<<std::min((nt + 127) / 128, 148 * 8), 128>>>(c.pos, n, kHitQueue, c.tbox_lo, c.tbox_hi, nt);
+        count_launch();
+        PPF_CUDA_TRY(cudaGetLastError());
+    }
+    PPF_CUDA_TRY(cudaStreamSynchronize(0));
     return PPF_OK;
 }
 
@@ -79,7 +172,8 @@ __device__ __forceinline__ PointN load_point(const float4 *__restrict__ pos, con
 // ---------------------------------------------------------------------------------
 // Debug / parity view: quantised features + keys of a tile (ppf_kernel + ppf_hash_kernel)
 // ---------------------------------------------------------------------------------
-__global__ void features_tile_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, int n,
+__global__ void features_tile_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm,
+                                     const uint32_t *__restrict__ inv, int n,
                                      float d_dist, float inv_d, unsigned df, int rb, int re, int ob, int oe,
                                      float4 *ppfs, uint32_t *keys) {
     size_t w = (size_t)(oe - ob), total = (size_t)(re - rb) * w;
@@ -92,7 +186,7 @@ __global__ void features_tile_kernel(const float4 *__restrict__ pos, const float
         } else if ((r % df) != 0 || r == o) {
             out.x = CUDART_NAN_F;                                    // kernel.cu:432-441
         } else {
-            PointN a = load_point(pos, nrm, r), b = load_point(pos, nrm, o);
+            PointN a = load_point(pos, nrm, inv ? inv[r] : r), b = load_point(pos, nrm, inv ? inv[o] : o);
             FeatureBins fb = pair_feature_bins(a, b, d_dist, inv_d);
             // kd == INT_MAX marks a distance more than 4e6 bins away: no table can hold it, so only
             // this debug view needs its quantised value; use the reference's own formula there.
@@ -123,7 +217,7 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
     if (ppfs_host) PPF_CUDA_TRY(cudaMalloc(&dp, total * sizeof(float4)));
     if (keys_host) PPF_CUDA_TRY(cudaMalloc(&dk, total * sizeof(uint32_t)));
     int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    features_tile_kernel<<<blocks, 256>>>(c.pos, c.nrm, c.n, d_dist, 1.0f / d_dist, df, rb, re, ob, oe, dp, dk);
+    features_tile_kernel<<<blocks, 256>>>(c.pos, c.nrm, c.inv, c.n, d_dist, 1.0f / d_dist, df, rb, re, ob, oe, dp, dk);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     if (dp) PPF_CUDA_TRY(cudaMemcpy(ppfs_host, dp, total * sizeof(float4), cudaMemcpyDeviceToHost));

@@ -39,13 +39,17 @@ __device__ __forceinline__ void mat4_invht(const Mat4 &T, Mat4 &Ti) {
 }
 
 __global__ void pose_kernel(const unsigned long long *__restrict__ votes, const float4 *mpos, const float4 *mnrm,
-                            const float4 *spos, const float4 *snrm, float *transforms, int count) {
+                            const float4 *spos, const float4 *snrm, const uint32_t *__restrict__ sinv, int ns,
+                            float *transforms, int count) {
     if (count <= 1) return;
     for (int idx = blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += gridDim.x * blockDim.x) {
         unsigned long long v = votes[idx];
         uint32_t s = (uint32_t)(v >> 32), mac = (uint32_t)v, m = mac >> 6, a = mac & 63u;
         if (s == 0 && m == 0 && a == 0) continue;
-        float4 mn = mnrm[m], sn = snrm[s], mp = mpos[m], sp = spos[s];
+        // survivors merged from other ranks are trusted to name valid points; guard against garbage anyway
+        if (s >= (uint32_t)ns) continue;
+        const uint32_t sp_i = sinv ? sinv[s] : s;                   // scene clouds are stored in Morton order
+        float4 mn = mnrm[m], sn = snrm[sp_i], mp = mpos[m], sp = spos[sp_i];
         float m_roty, m_rotz, s_roty, s_rotz;
         frame_angles(mn.x, mn.y, mn.z, m_roty, m_rotz);
         frame_angles(sn.x, sn.y, sn.z, s_roty, s_rotz);
@@ -321,7 +325,8 @@ int poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r) {
     if (K == 0) return PPF_OK;
     PPF_CUDA_TRY(cudaMemsetAsync(r.transformations, 0, (size_t)K * 64, 0));
     PPF_CUDA_TRY(cudaMemsetAsync(r.weighted, 0, (size_t)K * 4, 0));
-    pose_kernel<<<blocks_for(K), 256>>>(r.codes, m.cloud.pos, m.cloud.nrm, scene.pos, scene.nrm, r.transformations, K);
+    pose_kernel<<<blocks_for(K), 256>>>(r.codes, m.cloud.pos, m.cloud.nrm, scene.pos, scene.nrm, scene.inv, scene.n,
+                                        r.transformations, K);
     count_launch();
     weight_kernel<<<blocks_for(K), 256>>>(r.codes, r.counts, m.weights, r.weighted, K);
     count_launch();

@@ -31,7 +31,10 @@ namespace ppf {
 
 struct VoteArgs {
     // scene
-    const float4 *spos, *snrm, *sfy, *sfz;
+    const float4 *spos, *snrm, *sfy, *sfz;           // stored (Morton) order
+    const uint32_t *sinv;                            // caller's index -> stored position
+    const float4 *gbox_lo, *gbox_hi, *tbox_lo, *tbox_hi;
+    float cull_r2;                                   // squared distance beyond which no scene pair can hit the table
     int ns;
     int ref_start, ref_stride, ref_count;         // s_r = ref_start + k*ref_stride
     // model
@@ -123,6 +126,14 @@ __device__ __forceinline__ void vote_batch(const VoteCtx &c, const FrameYZ &FS, 
     }
 }
 
+// Squared distance from the reference point to an axis-aligned box (0 inside).  NaN boxes compare false
+// against the cull radius, i.e. are never culled.
+__device__ __forceinline__ float box_dist2(const PointN &R, float4 lo, float4 hi) {
+    float dx = fmaxf(fmaxf(lo.x - R.x, R.x - hi.x), 0.f), dy = fmaxf(fmaxf(lo.y - R.y, R.y - hi.y), 0.f),
+          dz = fmaxf(fmaxf(lo.z - R.z, R.z - hi.z), 0.f);
+    return dx * dx + dy * dy + dz * dz;
+}
+
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -144,13 +155,14 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     for (int i = tid; i < kNAlphaBins * S; i += THREADS) acc[i] = 0;
     if (tid == 0) { s_exact = 0; s_votes = 0; }
 
-    // reference point (registers) and its local frame
+    // reference point (registers) and its local frame; p_r = its position in the stored order
+    const int p_r = (int)__ldg(a.sinv + s_r);
     PointN R;
     {
-        float4 p = __ldg(a.spos + s_r), q = __ldg(a.snrm + s_r);
+        float4 p = __ldg(a.spos + p_r), q = __ldg(a.snrm + p_r);
         R.x = p.x; R.y = p.y; R.z = p.z; R.nx = q.x; R.ny = q.y; R.nz = q.z; R.nn = q.w;
     }
-    const FrameYZ FS = load_frame(a.sfy, a.sfz, s_r);
+    const FrameYZ FS = load_frame(a.sfy, a.sfz, p_r);
     VoteCtx ctx;
     ctx.map = a.map; ctx.mfy = a.mfy; ctx.mfz = a.mfz; ctx.mpos = a.mpos; ctx.spos = a.spos;
     ctx.nm = a.nm; ctx.chunk_base = chunk_base; ctx.stride = S; ctx.acc = acc;
@@ -158,6 +170,9 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     uint32_t my_exact = 0;
 
     for (int base = 0; base < a.ns; base += kHitQueue) {
+        // Tile culling (block-uniform): every scene pair (s_r, s_i) with s_i in this tile is longer than
+        // any model pair -> its distance bin is outside the table -> no hit; skip the tile altogether.
+        if (box_dist2(R, __ldg(a.tbox_lo + base / kHitQueue), __ldg(a.tbox_hi + base / kHitQueue)) >= a.cull_r2) continue;
         if (tid == 0) { s_nhits = 0; s_cur = 0; }
         for (int i = tid; i < kHitQueue; i += THREADS) cursor[i] = 0;
         __syncthreads();
@@ -167,7 +182,10 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             const int i = base + it * THREADS + tid;
             bool hit = false;
             uint4 h = make_uint4(0, 0, 0, 0);
-            if (i < a.ns && i != s_r) {
+            // warp culling: the 32 points of this warp are one Morton-compact group with a known AABB
+            const bool near = (i - lane) < a.ns &&
+                              box_dist2(R, __ldg(a.gbox_lo + (i >> 5)), __ldg(a.gbox_hi + (i >> 5))) < a.cull_r2;
+            if (near && i < a.ns && i != p_r) {
                 float4 p = __ldg(a.spos + i), q = __ldg(a.snrm + i);
                 PointN O;
                 O.x = p.x; O.y = p.y; O.z = p.z; O.nx = q.x; O.ny = q.y; O.nz = q.z; O.nn = q.w;
@@ -414,6 +432,7 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
     }
     r.K = 0;
     const int ns = scene.n;
+    if (ns > 0 && !scene.inv) { set_last_error("vote: the scene cloud has no spatial index"); return PPF_ERR_INVALID; }
     // reference points: every df-th scene point (kernel.cu:432), then every shard_count-th of those
     const int R_all = ns > 1 ? (ns + (int)df - 1) / (int)df : 0;     // ppf_kernel is a no-op for count <= 1
     const int R = R_all > shard_rank ? (R_all - shard_rank + shard_count - 1) / shard_count : 0;
@@ -425,6 +444,12 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         if (R == 0 || m.cloud.n <= 1 || m.K_d == 0) return PPF_OK;
         VoteArgs a;
         a.spos = scene.pos; a.snrm = scene.nrm; a.sfy = scene.fy; a.sfz = scene.fz; a.ns = ns;
+        a.sinv = scene.inv; a.gbox_lo = scene.gbox_lo; a.gbox_hi = scene.gbox_hi; a.tbox_lo = scene.tbox_lo; a.tbox_hi = scene.tbox_hi;
+        {   // a pair at true distance >= (K_d + 1) d_dist (1 + 1e-4) has distance bin >= K_d even after the approximate
+            // sqrt (relative error ~1e-6): it cannot be in the table.  Conservative: everything nearer is processed.
+            const float r = (float)(m.K_d + 1) * m.d_dist * 1.0001f;
+            a.cull_r2 = r * r;
+        }
         a.ref_start = shard_rank * (int)df; a.ref_stride = shard_count * (int)df; a.ref_count = R;
         a.mpos = m.cloud.pos; a.mfy = m.cloud.fy; a.mfz = m.cloud.fz; a.nm = m.cloud.n;
         a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
