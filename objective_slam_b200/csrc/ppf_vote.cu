@@ -271,29 +271,29 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             const uint32_t done = nfull * kVoteBatch;
             if (done < ngrab) {
                 const uint32_t n = ngrab - done;
-                for (uint32_t j0 = 0; j0 < n; j0 += 128) {
-                    uint32_t e[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t j = j0 + u * 32 + lane;
-                        e[u] = (j < n) ? __ldg(ent + done + j) : 0u;
-                    }
+                {
+                    // all (< 256) remaining entries are loaded before the first vote: one L2 latency, not two
                     uint32_t worst = 0, flags = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        const uint32_t j = j0 + u * 32 + lane;
+                    for (int u = 0; u < E; u++) {
+                        const uint32_t j = u * 32 + lane;
+                        e0[u] = (j < n) ? __ldg(ent + done + j) : 0u;
+                    }
+#pragma unroll
+                    for (int u = 0; u < E; u++) {
+                        const uint32_t j = u * 32 + lane;
                         if (j < n) {
                             uint32_t bin;
-                            worst = max(worst, alpha_bin_margin(hit_theta, e[u], bin));
-                            flags |= e[u];
-                            atomicAdd(&acc[bin * (uint32_t)S + (e[u] & kLocMask)], 1u);
+                            worst = max(worst, alpha_bin_margin(hit_theta, e0[u], bin));
+                            flags |= e0[u];
+                            atomicAdd(&acc[bin * (uint32_t)S + (e0[u] & kLocMask)], 1u);
                         }
                     }
                     if (worst >= kGuardSpan || (flags & kSlowBit)) {
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            const uint32_t j = j0 + u * 32 + lane;
-                            if (j < n) repair_vote(ctx, FS, hit_theta, h.w, e[u], pos_grab + done + j, my_exact);
+                        for (int u = 0; u < E; u++) {
+                            const uint32_t j = u * 32 + lane;
+                            if (j < n) repair_vote(ctx, FS, hit_theta, h.w, e0[u], pos_grab + done + j, my_exact);
                         }
                     }
                 }
