@@ -139,9 +139,9 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = a.chunk_rows, S = acc_stride(C);
     uint4 *queue = reinterpret_cast<uint4 *>(smem_raw);                               // [kHitQueue] hit records
-    uint32_t *cursor = reinterpret_cast<uint32_t *>(queue + kHitQueue);               // [kHitQueue] entries taken
-    uint32_t *acc = cursor + kHitQueue;                                               // [31][S] vote counters
-    __shared__ uint32_t s_nhits, s_cur, s_exact;
+    uint32_t *gstart = reinterpret_cast<uint32_t *>(queue + kHitQueue);               // [kHitQueue] first grab ticket of each hit
+    uint32_t *acc = gstart + kHitQueue;                                               // [31][S] vote counters
+    __shared__ uint32_t s_nhits, s_ticket, s_total, s_exact;
     __shared__ uint32_t s_red[32];
     __shared__ unsigned long long s_votes;
 
@@ -173,8 +173,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
         // Tile culling (block-uniform): every scene pair (s_r, s_i) with s_i in this tile is longer than
         // any model pair -> its distance bin is outside the table -> no hit; skip the tile altogether.
         if (box_dist2(R, __ldg(a.tbox_lo + base / kHitQueue), __ldg(a.tbox_hi + base / kHitQueue)) >= a.cull_r2) continue;
-        if (tid == 0) { s_nhits = 0; s_cur = 0; }
-        for (int i = tid; i < kHitQueue; i += THREADS) cursor[i] = 0;
+        if (tid == 0) { s_nhits = 0; s_ticket = 0; }
         __syncthreads();
         // ---- phase 1: pairs (s_r, s_i) of this tile -> hit queue
 #pragma unroll 1
@@ -212,24 +211,74 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             }
         }
         __syncthreads();
-        // ---- phase 2: all warps drain the queue in order, kVoteGrab entries per grab, so a
-        // 100k-entry bucket is shared by every warp instead of serialising one of them.
+        // ---- phase 1.5: ticket table.  Hit h owns the grab tickets [gstart[h], gstart[h+1]): one ticket per
+        // kVoteGrab of its entries (exclusive block scan of ceil(len / kVoteGrab) over the queue).
         const uint32_t nhits = s_nhits;
-        while (true) {
-            uint32_t hi = 0, off = 0;
-            if (lane == 0) {
-                hi = *(volatile uint32_t *)&s_cur;
-                while (hi < nhits) {
-                    const uint32_t len = queue[hi].y;
-                    off = atomicAdd(&cursor[hi], (uint32_t)kVoteGrab);
-                    if (off + kVoteGrab >= len) atomicMax(&s_cur, hi + 1);           // last (or past-last) grab
-                    if (off < len) break;
-                    hi = max(hi + 1, *(volatile uint32_t *)&s_cur);
-                }
+        {
+            constexpr int ITEMS = kHitQueue / THREADS;
+            uint32_t excl[ITEMS], sum = 0;
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) {
+                const uint32_t idx = tid * ITEMS + k;
+                excl[k] = sum;
+                sum += idx < nhits ? (queue[idx].y + kVoteGrab - 1) / kVoteGrab : 0u;
             }
-            hi = __shfl_sync(0xffffffffu, hi, 0);
-            if (hi >= nhits) break;
-            off = __shfl_sync(0xffffffffu, off, 0);
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            if (lane == 31) s_red[warp] = incl;
+            __syncthreads();
+            if (warp == 0) {
+                const uint32_t x = lane < THREADS / 32 ? s_red[lane] : 0u;
+                uint32_t inc2 = x;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if (lane >= o) inc2 += t;
+                }
+                s_red[lane] = inc2 - x;
+                if (lane == 31) s_total = inc2;
+            }
+            __syncthreads();
+            const uint32_t base_t = s_red[warp] + incl - sum;
+#pragma unroll
+            for (int k = 0; k < ITEMS; k++) {
+                const uint32_t idx = tid * ITEMS + k;
+                if (idx < nhits) gstart[idx] = base_t + excl[k];
+            }
+            __syncthreads();
+        }
+        // ---- phase 2: warps draw grab tickets; a ticket is one kVoteGrab-entry piece of one hit, so a
+        // 100k-entry bucket is shared by every warp, and no warp ever polls an exhausted hit.
+        const uint32_t total = s_total;
+        while (true) {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(&s_ticket, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= total) break;
+            // hit of ticket t = last h with gstart[h] <= t: two-level 32-wide search over <= 2048 hits
+            uint32_t hi, off;
+            {
+                const uint32_t i1 = (uint32_t)lane * (kHitQueue / 32);
+                const unsigned m1 = __ballot_sync(0xffffffffu, i1 < nhits && gstart[i1] <= t);
+                const uint32_t blk = (31u - (uint32_t)__clz((int)m1)) * (kHitQueue / 32);
+                uint32_t cnt = 0, g_found = 0;
+#pragma unroll
+                for (int r = 0; r < kHitQueue / 1024; r++) {
+                    const uint32_t i2 = blk + r * 32 + lane;
+                    const uint32_t g = i2 < nhits ? gstart[i2] : 0xFFFFFFFFu;
+                    const unsigned m2 = __ballot_sync(0xffffffffu, g <= t);
+                    if (m2) {                                                    // the last lane with g <= t holds gstart[hi]
+                        g_found = __shfl_sync(0xffffffffu, g, 31 - __clz((int)m2));
+                        cnt += __popc(m2);
+                    }
+                }
+                hi = blk + cnt - 1;
+                off = (t - g_found) * kVoteGrab;
+            }
             const uint4 h = queue[hi];
             const uint32_t ngrab = min((uint32_t)kVoteGrab, h.y - off);
             const uint32_t hit_theta = h.z | kLowOnes;                 // low 12 bits set: see alpha_bin_fast
