@@ -30,6 +30,9 @@ constexpr int kMaxChunkRows = 1504;          // 31 * (1504 + 1) * 4 B = 186,620 
 constexpr int kHitQueue     = 2048;          // 16 B record + 4 B cursor each
 constexpr int kVoteBatch    = 256;           // bucket entries per inner pass: 8 per lane, double-buffered in registers
 constexpr int kVoteGrab     = 2048;          // bucket entries one warp takes per scheduler grab
+// grouped vote kernel (ppf_vote_grouped.cu): a bigger hit queue (all hits of a reference point, sorted by
+// bucket) in exchange for a smaller accumulator chunk
+constexpr int kGroupedMaxRows = 480;         // 31 * (480 + 1) * 4 B = 59,644 B + 8,192 B entry stage + 13,312 hits x 12 B
 // accumulator row stride: chunk_rows is a multiple of 32, so +1 makes bank = (bin + row) mod 32 --
 // lanes that hit the same model point with different alpha bins (the common case inside a bucket,
 // whose entries are sorted by m_r) fall into different banks.

@@ -12,6 +12,7 @@
 //    gathered into bucket order once, so voting streams 4 B per vote.
 #include <cub/cub.cuh>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "../../include/ppf_b200.h"
@@ -352,7 +353,11 @@ int model_build(ModelTable &m) {
     }
     if (!(m.d_dist > 0.f)) { set_last_error("model: d_dist must be > 0"); return PPF_ERR_INVALID; }
     m.inv_d_dist = 1.0f / m.d_dist;
-    int max_rows = kMaxChunkRows;
+    // the grouped vote kernel trades accumulator rows for a bigger hit queue (ppf_internal.cuh)
+    int max_rows = kGroupedMaxRows;
+    if (const char *e = getenv("PPF_B200_VOTE")) {
+        if (!strcmp(e, "classic")) max_rows = kMaxChunkRows;
+    }
     if (const char *e = getenv("PPF_B200_CHUNK_ROWS")) {        // test hook: force more / smaller chunks
         int v = atoi(e);
         if (v >= 32 && v <= kMaxChunkRows) max_rows = v / 32 * 32;

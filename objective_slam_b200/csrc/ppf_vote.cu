@@ -22,117 +22,16 @@
 //     (count > thr * max, model.cu:164-167) using a monotone lower bound of the max.
 #include <cub/cub.cuh>
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 #include <vector>
 
 #include "../../include/ppf_b200.h"
 #include "ppf_internal.cuh"
 
+#include "ppf_vote_common.cuh"
+
 namespace ppf {
-
-struct VoteArgs {
-    // scene
-    const float4 *spos, *snrm, *sfy, *sfz;           // stored (Morton) order
-    const uint32_t *sinv;                            // caller's index -> stored position
-    const float4 *gbox_lo, *gbox_hi, *tbox_lo, *tbox_hi;
-    float cull_r2;                                   // squared distance beyond which no scene pair can hit the table
-    int ns;
-    int ref_start, ref_stride, ref_count;         // s_r = ref_start + k*ref_stride
-    // model
-    const float4 *mpos, *mfy, *mfz;
-    int nm;
-    float d_dist, inv_d;
-    int K_d;
-    uint32_t U;
-    const uint32_t *cell2bucket;
-    const uint2 *ranges;
-    const uint32_t *entries, *map;
-    int n_chunks, chunk_rows;
-    // output
-    float thr;
-    int emit_all;                                 // 1: emit every non-zero cell (vote histogram)
-    unsigned long long *cand_codes;
-    uint32_t *cand_counts;
-    uint32_t cand_cap;
-    uint32_t *scalars;                            // [0]=cand_n [1]=max [2]=(unused) [3]=exact-alpha votes
-    unsigned long long *totals;                   // [0]=votes cast [1]=non-zero cells
-};
-
-__device__ __forceinline__ FrameYZ load_frame(const float4 *__restrict__ fy, const float4 *__restrict__ fz, int i) {
-    float4 y = __ldg(fy + i), z = __ldg(fz + i);
-    FrameYZ f;
-    f.y[0] = y.x; f.y[1] = y.y; f.y[2] = y.z; f.y[3] = y.w;
-    f.z[0] = z.x; f.z[1] = z.y; f.z[2] = z.z; f.z[3] = z.w;
-    return f;
-}
-
-// Voting context shared by the fast and the exact path.
-struct VoteCtx {
-    const uint32_t *map;
-    const float4 *mfy, *mfz, *mpos, *spos;
-    int nm, chunk_base, stride;
-    uint32_t *acc;
-};
-
-// Exact alpha bin of one vote: rebuild u and v the way trans_model_scene does (kernel.cu:330-342).
-// Needed by ~1e-4 of the votes (guard band around the 30 bin edges, degenerate u or v); kept out of
-// line so that the hot loop stays small and free of divergence.
-__device__ __noinline__ uint32_t exact_vote_index(const VoteCtx &c, const FrameYZ &FS, uint32_t s_i, uint32_t entry,
-                                                  uint32_t pos) {
-    const uint32_t loc = entry & kLocMask;
-    const uint32_t pidx = __ldg(c.map + pos);
-    const int m_r = c.chunk_base + (int)loc;
-    const int m_i = (int)(pidx - (uint32_t)m_r * (uint32_t)c.nm);
-    const FrameYZ FM = load_frame(c.mfy, c.mfz, m_r);
-    const float4 mi = __ldg(c.mpos + m_i);
-    const float4 si = __ldg(c.spos + s_i);
-    float uy, uz, vy, vz;
-    frame_apply_yz(FM, mi.x, mi.y, mi.z, uy, uz);
-    frame_apply_yz(FS, si.x, si.y, si.z, vy, vz);
-    return alpha_bin_exact(uy, uz, vy, vz) * (uint32_t)c.stride + loc;
-}
-
-// The hot loop votes OPTIMISTICALLY: every entry of a batch adds 1 to the cell its fast alpha bin
-// names (always a valid cell), the guard-band margins are min-reduced and the slow flags OR-ed across
-// the batch (one VIADDMNMX and half a LOP3 per vote), and only when a batch contains a vote whose fast
-// bin is not provably the reference's (about one batch in 30) is it re-examined: such a vote is moved
-// from the optimistic cell to the exact one (-1 / +1 by the same thread, so no other thread can
-// observe a negative count, and phase 3 only reads after a barrier).  This removes the select, the
-// mask bookkeeping and all branches from the per-vote path.
-__device__ __forceinline__ void repair_vote(const VoteCtx &c, const FrameYZ &FS, uint32_t hit_ones, uint32_t s_i,
-                                            uint32_t entry, uint32_t pos, uint32_t &n_exact) {
-    uint32_t bin;
-    if (alpha_bin_margin(hit_ones, entry, bin) >= kGuardSpan || (entry & kSlowBit)) {
-        atomicSub(&c.acc[bin * (uint32_t)c.stride + (entry & kLocMask)], 1u);
-        atomicAdd(&c.acc[exact_vote_index(c, FS, s_i, entry, pos)], 1u);
-        n_exact++;
-    }
-}
-
-// One full batch: E entries per lane, entry u of this lane sits at table position pos_lane + 32 u.
-template <int E>
-__device__ __forceinline__ void vote_batch(const VoteCtx &c, const FrameYZ &FS, uint32_t hit_ones, uint32_t s_i,
-                                           const uint32_t (&e)[E], uint32_t pos_lane, uint32_t &n_exact) {
-    uint32_t worst = 0, flags = 0;
-#pragma unroll
-    for (int u = 0; u < E; u++) {
-        uint32_t bin;
-        worst = max(worst, alpha_bin_margin(hit_ones, e[u], bin));
-        flags |= e[u];
-        atomicAdd(&c.acc[bin * (uint32_t)c.stride + (e[u] & kLocMask)], 1u);
-    }
-    if (worst >= kGuardSpan || (flags & kSlowBit)) {
-#pragma unroll
-        for (int u = 0; u < E; u++) repair_vote(c, FS, hit_ones, s_i, e[u], pos_lane + 32 * u, n_exact);
-    }
-}
-
-// Squared distance from the reference point to an axis-aligned box (0 inside).  NaN boxes compare false
-// against the cull radius, i.e. are never culled.
-__device__ __forceinline__ float box_dist2(const PointN &R, float4 lo, float4 hi) {
-    float dx = fmaxf(fmaxf(lo.x - R.x, R.x - hi.x), 0.f), dy = fmaxf(fmaxf(lo.y - R.y, R.y - hi.y), 0.f),
-          dz = fmaxf(fmaxf(lo.z - R.z, R.z - hi.z), 0.f);
-    return dx * dx + dy * dy + dz * dz;
-}
 
 template <int THREADS>
 __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
@@ -281,72 +180,8 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
             }
             const uint4 h = queue[hi];
             const uint32_t ngrab = min((uint32_t)kVoteGrab, h.y - off);
-            const uint32_t hit_theta = h.z | kLowOnes;                 // low 12 bits set: see alpha_bin_fast
-            const bool force_exact = (h.z & kSlowBit) != 0;
             if (lane == 0) my_votes += ngrab;
-            const uint32_t pos_grab = h.x + off;
-            const uint32_t *__restrict__ ent = a.entries + pos_grab;
-            if (force_exact) {
-                // degenerate scene pair (v ~ 0): every vote of this hit takes the exact path
-                for (uint32_t j = lane; j < ngrab; j += 32) {
-                    atomicAdd(&acc[exact_vote_index(ctx, FS, h.w, __ldg(ent + j), pos_grab + j)], 1u);
-                    my_exact++;
-                }
-                continue;
-            }
-            // Full batches, software-pipelined: the 8 loads of batch b+1 are in flight while batch b votes.
-            constexpr int E = kVoteBatch / 32;
-            const uint32_t nfull = ngrab / kVoteBatch;
-            uint32_t e0[E], e1[E];
-            if (nfull) {
-#pragma unroll
-                for (int u = 0; u < E; u++) e0[u] = __ldg(ent + u * 32 + lane);
-            }
-            for (uint32_t bi = 0; bi < nfull; bi += 2) {
-                if (bi + 1 < nfull) {
-#pragma unroll
-                    for (int u = 0; u < E; u++) e1[u] = __ldg(ent + (bi + 1) * kVoteBatch + u * 32 + lane);
-                }
-                vote_batch<E>(ctx, FS, hit_theta, h.w, e0, pos_grab + bi * kVoteBatch + lane, my_exact);
-                if (bi + 1 < nfull) {
-                    if (bi + 2 < nfull) {
-#pragma unroll
-                        for (int u = 0; u < E; u++) e0[u] = __ldg(ent + (bi + 2) * kVoteBatch + u * 32 + lane);
-                    }
-                    vote_batch<E>(ctx, FS, hit_theta, h.w, e1, pos_grab + (bi + 1) * kVoteBatch + lane, my_exact);
-                }
-            }
-            // tail of the hit: fewer than kVoteBatch entries
-            const uint32_t done = nfull * kVoteBatch;
-            if (done < ngrab) {
-                const uint32_t n = ngrab - done;
-                {
-                    // all (< 256) remaining entries are loaded before the first vote: one L2 latency, not two
-                    uint32_t worst = 0, flags = 0;
-#pragma unroll
-                    for (int u = 0; u < E; u++) {
-                        const uint32_t j = u * 32 + lane;
-                        e0[u] = (j < n) ? __ldg(ent + done + j) : 0u;
-                    }
-#pragma unroll
-                    for (int u = 0; u < E; u++) {
-                        const uint32_t j = u * 32 + lane;
-                        if (j < n) {
-                            uint32_t bin;
-                            worst = max(worst, alpha_bin_margin(hit_theta, e0[u], bin));
-                            flags |= e0[u];
-                            atomicAdd(&acc[bin * (uint32_t)S + (e0[u] & kLocMask)], 1u);
-                        }
-                    }
-                    if (worst >= kGuardSpan || (flags & kSlowBit)) {
-#pragma unroll
-                        for (int u = 0; u < E; u++) {
-                            const uint32_t j = u * 32 + lane;
-                            if (j < n) repair_vote(ctx, FS, hit_theta, h.w, e0[u], pos_grab + done + j, my_exact);
-                        }
-                    }
-                }
-            }
+            vote_single_hit(ctx, FS, a.entries, h.z, h.w, h.x + off, ngrab, lane, my_exact);
         }
         __syncthreads();
     }
@@ -487,6 +322,12 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
     const int R = R_all > shard_rank ? (R_all - shard_rank + shard_count - 1) / shard_count : 0;
     if (pairs_out) *pairs_out = (unsigned long long)R * (unsigned long long)ns;
     if (launches) *launches = 0;
+    // kernel choice: the grouped kernel needs the smaller accumulator chunk the model build gives it by
+    // default (PPF_B200_VOTE=classic at build time keeps 1504-row chunks and the one-hit-per-pass kernel)
+    bool use_grouped = vote_grouped_supported(m, ns);
+    if (const char *e = getenv("PPF_B200_VOTE")) {
+        if (!strcmp(e, "classic")) use_grouped = false;
+    }
     for (int attempt = 0; attempt < 8; attempt++) {
         PPF_CUDA_TRY(cudaMemsetAsync(r.scalars, 0, 4 * sizeof(uint32_t), 0));
         PPF_CUDA_TRY(cudaMemsetAsync(r.votes_total, 0, 2 * sizeof(unsigned long long), 0));
@@ -504,13 +345,17 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
         a.cell2bucket = m.cell2bucket; a.ranges = m.ranges; a.entries = m.entries; a.map = m.map;
         a.n_chunks = m.n_chunks; a.chunk_rows = m.chunk_rows;
+        a.queue_cap = 0; a.n_splits = 1;
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;
         a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
         a.scalars = r.scalars; a.totals = r.votes_total;
         const size_t smem = (size_t)kNAlphaBins * acc_stride(m.chunk_rows) * 4 + (size_t)kHitQueue * (sizeof(uint4) + 4);
         const long long grid = (long long)R * m.n_chunks;
         if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, chunk) CTAs"); return PPF_ERR_UNSUPPORTED; }
-        if (smem > 113 * 1024) {
+        if (use_grouped) {
+            int rc = vote_grouped_launch(a, R);
+            if (rc) return rc;
+        } else if (smem > 113 * 1024) {
             PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             vote_kernel<1024><<<(unsigned)grid, 1024, smem>>>(a);
             count_launch();

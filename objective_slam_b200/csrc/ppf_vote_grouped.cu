@@ -1,0 +1,537 @@
+// ppf_vote_grouped.cu -- voting_scheme, second formulation of the fused vote kernel.
+// Same contract as vote_kernel (ppf_vote.cu: replaces Scene::Scene's ppf_kernel / ppf_hash_kernel pass
+// scene.cu:24-55, ParallelHashArray::GetIndices parallel_hash_array.hpp:81-92, ppf_vote_count_kernel,
+// ppf_vote_kernel kernel.cu:480-554 and the sort / histogram tail of Model::ComputeUniqueVotes
+// model.cu:148-170), same accumulator cells, same bit-exact fast / exact alpha logic.
+//
+// What changes is WHO shares an ATOMS.  A reference point hits the same bucket many times (on the
+// configs[1] workload the vote-weighted multiplicity is ~40): the classical loop lets the 32 lanes of
+// a warp read 32 different entries of the bucket for ONE hit, so one ATOMS touches several accumulator
+// rows (bank = (bin + row) mod 32 -> 1.8 wavefronts per ATOMS measured) and every entry is fetched and
+// decoded once per hit.  Here
+//   * one CTA owns one scene reference point: ALL its hits are collected once (phase 1), sorted by
+//     bucket in shared memory (bitonic sort of 8-byte records), and reused for every model chunk;
+//   * a bucket hit h times is cut into pieces of 32 / 16 / 8 hits (+ single hits for the rest);
+//     a warp votes HG hits x (32 / HG) entries per ATOMS: the lanes of one ATOMS fall into one or two
+//     accumulator rows (conflict-free by the row stride, equal cells merged by ATOMS.POPC.INC), an
+//     entry is fetched once per HG hits and decoded once (staged in shared memory as
+//     (entry, row address)), and a vote costs 5 instructions (IADD, IMAD.WIDE, VIADDMNMX, IMAD, ATOMS)
+//     + half an LDS.128;
+//   * the accumulator chunk is small (<= 480 model points x 31 bins) so that the queue holds 13,312
+//     hits; a reference point with more hits than that falls back to re-collecting its hits per chunk.
+// tools/microbench/grouped_vote.cu: 14.2 / 11-13 / 9-11 votes/clk/SM at HG = 32 / 16 / 8 against 6.1 for
+// the classical loop inside the full kernel.
+#include <algorithm>
+#include <cstdlib>
+
+#include "ppf_vote_common.cuh"
+
+namespace ppf {
+
+constexpr uint32_t kGTile       = kHitQueue;        // scene points per phase-1 tile (the scene's tile AABBs)
+constexpr int      kGStage      = 64;               // entries staged per warp per block (two per lane)
+constexpr uint32_t kGGrabVotes  = 8192;             // votes per scheduler ticket of a grouped piece
+constexpr int      kGItemsMax   = 16;               // queue records per thread in the ticket scan
+// hit record: [bucket : 20 | (theta_v + half) : 20 | slow : 1 | stored scene index : 23]
+constexpr int      kGBucketShift = 44;
+constexpr int      kGThetaShift  = 24;
+constexpr uint32_t kGIndexMask   = (1u << 23) - 1u;
+constexpr size_t   kGSmemMax     = 227 * 1024 - 512;  // opt-in maximum minus the kernel's static shared memory
+
+static size_t acc_bytes(int chunk_rows) { return ((size_t)kNAlphaBins * acc_stride(chunk_rows) * 4 + 15) & ~(size_t)15; }
+
+// Largest hit queue (multiple of 1024 records, 12 B each) that fits next to the accumulator.
+int vote_grouped_queue_cap(int chunk_rows) {
+    const size_t fixed = (size_t)32 * kGStage * sizeof(uint2) + acc_bytes(chunk_rows);
+    if (fixed + 1024 * 12 > kGSmemMax) return 0;
+    const size_t q = (kGSmemMax - fixed) / 12 / 1024 * 1024;
+    return (int)std::min<size_t>(q, (size_t)kGItemsMax * 1024);
+}
+size_t vote_grouped_smem(int chunk_rows) {
+    return (size_t)vote_grouped_queue_cap(chunk_rows) * 12 + (size_t)32 * kGStage * sizeof(uint2) + acc_bytes(chunk_rows);
+}
+bool vote_grouped_supported(const ModelTable &m, int ns) {
+    return m.chunk_rows <= kGroupedMaxRows && m.U < (1u << 20) && ns <= (int)kGIndexMask &&
+           vote_grouped_queue_cap(m.chunk_rows) >= 2 * (int)kGTile;
+}
+
+// piece code: 0 = single hit (classical loop), c = 1..3 -> 2^(c+2) = 8 / 16 / 32 hits
+__device__ __forceinline__ uint32_t piece_hits(uint32_t code) { return code ? (4u << code) : 1u; }
+__device__ __forceinline__ uint32_t piece_grab(uint32_t code) { return code ? (kGGrabVotes >> (code + 2)) : (uint32_t)kVoteGrab; }
+
+struct GroupCtx {
+    const unsigned long long *queue;
+    uint2 *stage;                                   // this warp's kGStage staging slots
+    uint32_t trash_addr;                            // pad column of the accumulator (bin 0)
+};
+
+// One ticket of a grouped piece: HG = 4 << code hits queue[i0 .. i0 + HG) x entries [pos_grab, pos_grab + ngrab).
+// Lane l votes for hit l % HG and belongs to entry group g = l / HG (EG = 32 / HG groups).  A block is 64
+// consecutive entries (two coalesced loads per lane); group g owns K = 2 HG of them: its position 2m holds
+// entry m EG + g and position 2m + 1 entry 32 + m EG + g, so that (a) the lane that loaded entries l and
+// l + 32 stages both with one STS.128, (b) a lane reads two positions per LDS.128 and (c) at every step the
+// EG groups vote for EG ADJACENT entries, which mostly share m_r (a bucket is sorted by m_r): the lanes of
+// one ATOMS fall into one or two accumulator rows.  HG is a run-time value on purpose: one copy of the loop
+// serves every piece size (separate instantiations thrashed the instruction cache: 58% no-instruction stalls).
+__device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx &gc, const FrameYZ &FS, uint32_t i0,
+                                             uint32_t code, const uint32_t *__restrict__ entries, uint32_t pos_grab,
+                                             uint32_t ngrab, int lane, uint32_t &n_exact) {
+    const uint32_t lhg = code + 2u;                 // log2(HG)
+    const uint32_t HG = 1u << lhg, EG = 32u >> lhg, K = 2u * HG;
+    const uint32_t g = (uint32_t)lane >> lhg;
+    const unsigned long long rec = gc.queue[i0 + ((uint32_t)lane & (HG - 1u))];
+    const uint32_t hit_ones = ((uint32_t)(rec >> kGThetaShift) << kThetaShift) | kLowOnes;
+    const bool hit_slow = ((uint32_t)rec >> 23) & 1u;
+    const uint32_t s_i = (uint32_t)rec & kGIndexMask;
+    const uint32_t S4 = (uint32_t)ctx.stride * 4u;
+    const uint32_t trash = gc.trash_addr;
+    // this lane loads entries l and l + 32 of a block: group l % EG, positions 2 (l / EG) and 2 (l / EG) + 1
+    uint4 *my_slot = reinterpret_cast<uint4 *>(gc.stage + (((uint32_t)lane & (EG - 1u)) * K + 2u * ((uint32_t)lane / EG)));
+    const uint2 *grp = gc.stage + g * K;
+    const uint4 *src = reinterpret_cast<const uint4 *>(grp);
+    const uint32_t *__restrict__ ent = entries + pos_grab + lane;
+
+    // exact recount of the staged positions [p0, p1) of this lane's group (rare)
+    auto repair = [&](uint32_t p0, uint32_t p1, uint32_t blk_pos) {
+#pragma unroll 1
+        for (uint32_t p = p0; p < p1; p++) {
+            const uint2 r = grp[p];
+            uint32_t bin;
+            const uint32_t margin = alpha_bin_margin(hit_ones, r.x, bin);
+            if (r.y != trash && (margin >= kGuardSpan || (r.x & kSlowBit) || hit_slow)) {
+                const uint32_t j = (p & 1u) * 32u + (p >> 1) * EG + g;          // entry index within the block
+                atomicSub(&ctx.acc[bin * (uint32_t)ctx.stride + (r.x & kLocMask)], 1u);
+                atomicAdd(&ctx.acc[exact_vote_index(ctx, FS, s_i, r.x, blk_pos + j)], 1u);
+                n_exact++;
+            }
+        }
+    };
+    auto vote2 = [&](const uint4 q, uint32_t &worst) {
+        {
+            const unsigned long long p = (unsigned long long)(hit_ones - q.x) * (unsigned long long)kNAngle;
+            worst = max(worst, (uint32_t)p - kGuardLoA);
+            red_shared_inc((uint32_t)(p >> 32) * S4 + q.y);
+        }
+        {
+            const unsigned long long p = (unsigned long long)(hit_ones - q.z) * (unsigned long long)kNAngle;
+            worst = max(worst, (uint32_t)p - kGuardLoA);
+            red_shared_inc((uint32_t)(p >> 32) * S4 + q.w);
+        }
+    };
+
+    // the entries of the next two blocks are in flight while a block votes
+    const uint32_t nblocks = (ngrab + 63u) / 64u;
+    uint32_t c0, c1, n0, n1, m0, m1;
+    {
+        const uint32_t l = (uint32_t)lane;
+        c0 = l < ngrab ? __ldg(ent) : 0u;              c1 = l + 32u < ngrab ? __ldg(ent + 32) : 0u;
+        n0 = l + 64u < ngrab ? __ldg(ent + 64) : 0u;   n1 = l + 96u < ngrab ? __ldg(ent + 96) : 0u;
+    }
+#pragma unroll 1
+    for (uint32_t blk = 0; blk < nblocks; blk++) {
+        const uint32_t blk0 = blk * 64u;               // first entry of this block within the grab
+        {
+            const uint32_t j = blk0 + 128u + (uint32_t)lane;
+            m0 = j < ngrab ? __ldg(ent + blk0 + 128) : 0u;
+            m1 = j + 32u < ngrab ? __ldg(ent + blk0 + 160) : 0u;
+        }
+        const uint32_t nvalid = min(64u, ngrab - blk0);
+        uint32_t a0 = ctx.acc_addr + (c0 & kLocMask) * 4u, a1 = ctx.acc_addr + (c1 & kLocMask) * 4u;
+        bool slow = ((c0 | c1) & kSlowBit) != 0u;
+        if (nvalid < 64u) {
+            if ((uint32_t)lane >= nvalid) { a0 = trash; c0 = 0u; }
+            if ((uint32_t)lane + 32u >= nvalid) { a1 = trash; c1 = 0u; }
+            slow = ((c0 | c1) & kSlowBit) != 0u;
+        }
+        __syncwarp();
+        *my_slot = make_uint4(c0, a0, c1, a1);
+        const unsigned slowmask = __ballot_sync(0xffffffffu, slow);
+        __syncwarp();
+        const uint32_t worst0 = (hit_slow || slowmask) ? 0xFFFFFFFFu : 0u;
+        if (nvalid == 64u) {
+            // sub-batches of 8 positions (4 LDS.128), one guard-band test each
+#pragma unroll 1
+            for (uint32_t p = 0; p < K; p += 8) {
+                const uint4 q0 = src[p / 2], q1 = src[p / 2 + 1], q2 = src[p / 2 + 2], q3 = src[p / 2 + 3];
+                uint32_t worst = worst0;
+                vote2(q0, worst); vote2(q1, worst); vote2(q2, worst); vote2(q3, worst);
+                if (worst >= kGuardSpan) repair(p, p + 8, pos_grab + blk0);
+            }
+        } else {
+            // last, partial block: the first 32 entries sit at the even positions, so pairs past
+            // ceil(min(nvalid, 32) / EG) hold nothing; invalid slots inside a pair point at the pad column
+            const uint32_t pairs = (min(nvalid, 32u) + EG - 1u) / EG;
+            uint32_t worst = worst0;
+#pragma unroll 1
+            for (uint32_t k = 0; k < pairs; k++) {
+                const uint4 q = src[k];
+                {
+                    const unsigned long long p = (unsigned long long)(hit_ones - q.x) * (unsigned long long)kNAngle;
+                    if (q.y != trash) worst = max(worst, (uint32_t)p - kGuardLoA);
+                    red_shared_inc((uint32_t)(p >> 32) * S4 + q.y);
+                }
+                {
+                    const unsigned long long p = (unsigned long long)(hit_ones - q.z) * (unsigned long long)kNAngle;
+                    if (q.w != trash) worst = max(worst, (uint32_t)p - kGuardLoA);
+                    red_shared_inc((uint32_t)(p >> 32) * S4 + q.w);
+                }
+            }
+            if (worst >= kGuardSpan) repair(0, 2u * pairs, pos_grab + blk0);
+        }
+        c0 = n0; c1 = n1; n0 = m0; n1 = m1;
+    }
+}
+
+// first index i < n with (gend[i] >> 3) > t; the caller guarantees that one exists (n <= 16384)
+__device__ __forceinline__ uint32_t ticket_owner(const uint32_t *gend, uint32_t n, uint32_t t, int lane) {
+    const uint32_t key = (t << 3) | 7u;                          // gend[i] > key  <=>  (gend[i] >> 3) > t
+    uint32_t base = 0;
+    if (n > 1024u) {                                             // 32 blocks of 512, then 32 of 16, then 16
+        const unsigned m = __ballot_sync(0xffffffffu, gend[min((uint32_t)lane * 512u + 511u, n - 1u)] > key);
+        base = (uint32_t)(__ffs((int)m) - 1) * 512u;
+        const unsigned m1 = __ballot_sync(0xffffffffu, gend[min(base + (uint32_t)lane * 16u + 15u, n - 1u)] > key);
+        base += (uint32_t)(__ffs((int)m1) - 1) * 16u;
+        const unsigned m2 = __ballot_sync(0xffffffffu, lane < 16 && gend[min(base + (uint32_t)lane, n - 1u)] > key);
+        return base + (uint32_t)(__ffs((int)m2) - 1);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, gend[min((uint32_t)lane * 32u + 31u, n - 1u)] > key);
+    base = (uint32_t)(__ffs((int)m) - 1) * 32u;
+    const unsigned m2 = __ballot_sync(0xffffffffu, gend[min(base + (uint32_t)lane, n - 1u)] > key);
+    return base + (uint32_t)(__ffs((int)m2) - 1);
+}
+
+// first index in queue[0, n) whose record is >= key
+__device__ __forceinline__ uint32_t queue_lower_bound(const unsigned long long *queue, uint32_t n, unsigned long long key) {
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (queue[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+template <int THREADS>
+__global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int C = a.chunk_rows, S = acc_stride(C);
+    const uint32_t Q = (uint32_t)a.queue_cap;
+    unsigned long long *queue = reinterpret_cast<unsigned long long *>(smem_raw);        // [Q] hit records
+    uint32_t *gend = reinterpret_cast<uint32_t *>(queue + Q);                             // [Q] ticket table
+    uint2 *stage_all = reinterpret_cast<uint2 *>(gend + Q);                               // [32 warps][kGStage]
+    uint32_t *acc = reinterpret_cast<uint32_t *>(stage_all + 32 * kGStage);               // [31][S] vote counters
+    __shared__ uint32_t s_nhits, s_ticket, s_total, s_exact;
+    __shared__ uint32_t s_red[32];
+    __shared__ unsigned long long s_votes;
+    // reference point and its frame: only phase 1 and the exact-alpha path read them, so they live in
+    // shared memory and not in 15 registers of the vote loop
+    __shared__ PointN s_R;
+    __shared__ FrameYZ s_FS;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int split = blockIdx.x / a.ref_count;
+    const int refk = blockIdx.x - split * a.ref_count;
+    const int s_r = a.ref_start + refk * a.ref_stride;
+    const int cps = (a.n_chunks + a.n_splits - 1) / a.n_splits;
+    const int c0 = split * cps, c1 = min(a.n_chunks, c0 + cps);
+    if (c0 >= c1) return;
+
+    for (int i = tid; i < kNAlphaBins * S; i += THREADS) acc[i] = 0;
+    if (tid == 0) { s_exact = 0; s_votes = 0; s_nhits = 0; }
+
+    const int p_r = (int)__ldg(a.sinv + s_r);
+    if (tid == 0) {
+        float4 p = __ldg(a.spos + p_r), q = __ldg(a.snrm + p_r);
+        PointN R;
+        R.x = p.x; R.y = p.y; R.z = p.z; R.nx = q.x; R.ny = q.y; R.nz = q.z; R.nn = q.w;
+        s_R = R;
+        s_FS = load_frame(a.sfy, a.sfz, p_r);
+    }
+    const FrameYZ &FS = s_FS;
+    VoteCtx ctx;
+    ctx.map = a.map; ctx.mfy = a.mfy; ctx.mfz = a.mfz; ctx.mpos = a.mpos; ctx.spos = a.spos;
+    ctx.nm = a.nm; ctx.chunk_base = 0; ctx.stride = S; ctx.acc = acc;
+    ctx.acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
+    GroupCtx gc;
+    gc.queue = queue; gc.stage = stage_all + warp * kGStage; gc.trash_addr = ctx.acc_addr + (uint32_t)C * 4u;
+    unsigned long long my_votes = 0;
+    uint32_t my_exact = 0;
+    const int items = (int)(Q / THREADS);
+    unsigned long long heads = 0;                   // 4 bits per owned queue record: head << 3 | piece code
+    __syncthreads();
+
+    // ---- phase 1 for one tile of scene points: pairs (s_r, s_i) -> hit queue (tile / warp culling as in
+    // vote_kernel).  flt != nullptr keeps only hits whose bucket has entries in that chunk.
+    auto collect_tile = [&](uint32_t base, const uint2 *__restrict__ flt) {
+        const PointN R = s_R;
+        const FrameYZ FS = s_FS;
+        if (box_dist2(R, __ldg(a.tbox_lo + base / kGTile), __ldg(a.tbox_hi + base / kGTile)) >= a.cull_r2) return;
+#pragma unroll 1
+        for (uint32_t it = 0; it < kGTile / THREADS; it++) {
+            const int i = (int)(base + it * THREADS) + tid;
+            bool hit = false;
+            unsigned long long h = 0;
+            const bool near = (i - lane) < a.ns &&
+                              box_dist2(R, __ldg(a.gbox_lo + (i >> 5)), __ldg(a.gbox_hi + (i >> 5))) < a.cull_r2;
+            if (near && i < a.ns && i != p_r) {
+                float4 p = __ldg(a.spos + i), q = __ldg(a.snrm + i);
+                PointN O;
+                O.x = p.x; O.y = p.y; O.z = p.z; O.nx = q.x; O.ny = q.y; O.nz = q.z; O.nn = q.w;
+                FeatureBins fb = pair_feature_bins(R, O, a.d_dist, a.inv_d);
+                if (fb.kd >= 0 && fb.kd < a.K_d) {
+                    const uint32_t b = __ldg(a.cell2bucket + cell_index(fb.kd, fb.k1, fb.k2, fb.k3));
+                    if (b != kNoBucket && (flt == nullptr || __ldg(flt + b).y != 0u)) {
+                        float vy, vz;
+                        frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
+                        const uint32_t tc = theta_code(vy, vz);
+                        const uint32_t th = ((tc & kThetaMask) + kThetaHalf) & kThetaMask;
+                        h = ((unsigned long long)b << kGBucketShift) | ((unsigned long long)th << kGThetaShift) |
+                            ((unsigned long long)(tc >> 31) << 23) | (unsigned long long)(uint32_t)i;
+                        hit = true;
+                    }
+                }
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, hit);
+            if (m) {
+                uint32_t slot = 0;
+                if (lane == 0) slot = atomicAdd(&s_nhits, (uint32_t)__popc(m));
+                slot = __shfl_sync(0xffffffffu, slot, 0) + __popc(m & ((1u << lane) - 1u));
+                if (hit && slot < Q) queue[slot] = h;            // the first pass may overflow: it only counts then
+            }
+        }
+    };
+
+    // ---- sort queue[0, n) (bitonic network with the mirrored first stage of every merge: every exchange
+    // is ascending, so n need not be a power of two) and cut the bucket groups into pieces.
+    auto sort_and_cut = [&](uint32_t n) {
+        uint32_t P = 2;
+        while (P < n) P <<= 1;
+        for (uint32_t k = 2; k <= P; k <<= 1) {
+            const uint32_t hk = k >> 1;
+            for (uint32_t t = tid; t < P / 2; t += THREADS) {
+                const uint32_t blk = (t / hk) * k, o = t & (hk - 1u);
+                const uint32_t i = blk + o, l = blk + k - 1u - o;
+                if (l < n) {
+                    const unsigned long long x = queue[i], y = queue[l];
+                    if (x > y) { queue[i] = y; queue[l] = x; }
+                }
+            }
+            __syncthreads();
+            for (uint32_t j = hk >> 1; j > 0; j >>= 1) {
+                for (uint32_t t = tid; t < P / 2; t += THREADS) {
+                    const uint32_t i = ((t & ~(j - 1u)) << 1) | (t & (j - 1u)), l = i + j;
+                    if (l < n) {
+                        const unsigned long long x = queue[i], y = queue[l];
+                        if (x > y) { queue[i] = y; queue[l] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        }
+        // A bucket hit h times: h / 32 pieces of 32 hits, then 16 / 8 by the bits of the remainder, then
+        // single hits.
+        heads = 0;
+        for (int k = 0; k < items; k++) {
+            const uint32_t idx = (uint32_t)(tid * items + k);
+            if (idx >= n) break;
+            const uint32_t b = (uint32_t)(queue[idx] >> kGBucketShift);
+            const uint32_t lo = queue_lower_bound(queue, n, (unsigned long long)b << kGBucketShift);
+            const uint32_t hi = queue_lower_bound(queue, n, (unsigned long long)(b + 1u) << kGBucketShift);
+            const uint32_t h = hi - lo, o = idx - lo, full = h & ~31u;
+            uint32_t hc = 0;                                       // head << 3 | code
+            if (o < full) { if ((o & 31u) == 0u) hc = 8u | 3u; }
+            else {
+                const uint32_t r = h - full, q = o - full;
+                const uint32_t p16 = r & 16u, p8 = r & 8u;
+                if (p16 && q == 0u) hc = 8u | 2u;
+                else if (p8 && q == p16) hc = 8u | 1u;
+                else if (q >= p16 + p8) hc = 8u;
+            }
+            heads |= (unsigned long long)hc << (4 * k);
+        }
+    };
+
+    // ---- votes of the sorted queue[0, n) against chunk c
+    auto vote_chunk = [&](uint32_t n, const uint2 *__restrict__ ranges) {
+        // tickets: the head of a piece owns ceil(slice length / grab); gend = inclusive prefix << 3 | code
+        uint32_t sum = 0;
+        for (int k = 0; k < items; k++) {
+            const uint32_t idx = (uint32_t)(tid * items + k);
+            if (idx >= n) break;
+            const uint32_t hc = (uint32_t)(heads >> (4 * k)) & 15u;
+            if (hc & 8u) {
+                const uint32_t len = __ldg(ranges + (uint32_t)(queue[idx] >> kGBucketShift)).y;
+                const uint32_t grab = piece_grab(hc & 7u);
+                sum += (len + grab - 1u) / grab;
+            }
+            gend[idx] = (sum << 3) | (hc & 7u);
+        }
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) s_red[warp] = incl;
+        if (tid == 0) s_ticket = 0;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t x = lane < THREADS / 32 ? s_red[lane] : 0u;
+            uint32_t inc2 = x;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += t;
+            }
+            s_red[lane] = inc2 - x;
+            if (lane == 31) s_total = inc2;
+        }
+        __syncthreads();
+        const uint32_t off_t = (s_red[warp] + incl - sum) << 3;
+        for (int k = 0; k < items; k++) {
+            const uint32_t idx = (uint32_t)(tid * items + k);
+            if (idx >= n) break;
+            gend[idx] += off_t;
+        }
+        __syncthreads();
+        const uint32_t total = s_total;
+        while (true) {
+            uint32_t t = 0;
+            if (lane == 0) t = atomicAdd(&s_ticket, 1u);
+            t = __shfl_sync(0xffffffffu, t, 0);
+            if (t >= total) break;
+            const uint32_t i0 = ticket_owner(gend, n, t, lane);
+            const uint32_t code = gend[i0] & 7u;
+            const uint32_t gstart = i0 ? (gend[i0 - 1u] >> 3) : 0u;
+            const unsigned long long rec = queue[i0];
+            const uint2 rg = __ldg(ranges + (uint32_t)(rec >> kGBucketShift));
+            const uint32_t off = (t - gstart) * piece_grab(code);
+            const uint32_t ngrab = min(piece_grab(code), rg.y - off);
+            if (lane == 0) my_votes += (unsigned long long)ngrab * piece_hits(code);
+            const uint32_t pos_grab = rg.x + off;
+            if (code == 0u) {
+                const uint32_t hit_word = ((uint32_t)(rec >> kGThetaShift) << kThetaShift) |
+                                          ((((uint32_t)rec >> 23) & 1u) << kLocBits);
+                vote_single_hit<true>(ctx, FS, a.entries, hit_word, (uint32_t)rec & kGIndexMask, pos_grab, ngrab, lane, my_exact);
+            } else {
+                vote_grouped(ctx, gc, FS, i0, code, a.entries, pos_grab, ngrab, lane, my_exact);
+            }
+        }
+        __syncthreads();
+    };
+
+    // ---- first pass: all hits of the reference point, whatever the chunk
+    for (uint32_t base = 0; base < (uint32_t)a.ns; base += kGTile) collect_tile(base, nullptr);
+    __syncthreads();
+    const uint32_t n_all = s_nhits;
+    const bool single = n_all <= Q;                 // the common case: one collection + one sort serve every chunk
+
+    for (int c = c0; c < c1; c++) {
+        const uint2 *__restrict__ ranges = a.ranges + (size_t)c * a.U;
+        ctx.chunk_base = c * C;
+        uint32_t base = 0;
+        while (true) {
+            uint32_t n = n_all;
+            if (!single) {
+                // more hits than the queue holds: collect the hits of THIS chunk tile by tile and vote
+                // whenever the queue cannot take another tile
+                __syncthreads();
+                if (tid == 0) s_nhits = 0;
+                __syncthreads();
+                while (base < (uint32_t)a.ns && s_nhits + kGTile <= Q) {
+                    collect_tile(base, ranges);
+                    base += kGTile;
+                    __syncthreads();
+                }
+                n = s_nhits;
+            }
+            if (n) {
+                if (!single || c == c0) sort_and_cut(n);
+                vote_chunk(n, ranges);
+            }
+            if (single || base >= (uint32_t)a.ns) break;
+        }
+        __syncthreads();
+        // ---- phase 3 for this chunk: block max, statistics, emission of candidate cells, reset.
+        // (the pad column is scratch: partial blocks vote into it)
+        uint32_t lmax = 0, nz = 0;
+        for (int i = tid; i < kNAlphaBins * S; i += THREADS) {
+            uint32_t v = acc[i];
+            if ((i % S) == C) v = 0;
+            lmax = max(lmax, v);
+            nz += (v != 0);
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            lmax = max(lmax, __shfl_xor_sync(0xffffffffu, lmax, o));
+            nz += __shfl_xor_sync(0xffffffffu, nz, o);
+        }
+        if (lane == 0) {
+            s_red[warp] = lmax;
+            if (nz) atomicAdd(&a.totals[1], (unsigned long long)nz);
+        }
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = (lane < THREADS / 32) ? s_red[lane] : 0;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+            if (lane == 0) {
+                const uint32_t old = v ? atomicMax(&a.scalars[1], v) : 0u;
+                s_red[0] = max(old, v);
+            }
+        }
+        __syncthreads();
+        const uint32_t bound = s_red[0];                       // <= final global max
+        const float min_votecount = a.emit_all ? 0.0f : a.thr * (float)bound;     // model.cu:164
+        for (int i = tid; i < kNAlphaBins * S; i += THREADS) {
+            const uint32_t v = acc[i];
+            if (v == 0) continue;
+            acc[i] = 0;
+            const uint32_t bin = i / S, loc = i - bin * S;
+            if ((int)loc != C && (float)v > min_votecount) {
+                const uint32_t slot = atomicAdd(&a.scalars[0], 1u);
+                if (slot < a.cand_cap) {
+                    // [scene ref : 32 | model point : 26 | alpha : 6]   (kernel.cu:548-549, model.h:61-63)
+                    a.cand_codes[slot] = ((unsigned long long)(uint32_t)s_r << 32) |
+                                         (unsigned long long)((((uint32_t)(c * C) + loc) << 6) | bin);
+                    a.cand_counts[slot] = v;
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+#pragma unroll
+    for (int o = 16; o; o >>= 1) my_exact += __shfl_xor_sync(0xffffffffu, my_exact, o);
+    if (lane == 0) {
+        if (my_votes) atomicAdd(&s_votes, my_votes);
+        if (my_exact) atomicAdd(&s_exact, my_exact);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        if (s_votes) atomicAdd(&a.totals[0], s_votes);
+        if (s_exact) atomicAdd(&a.scalars[3], s_exact);
+    }
+}
+
+int vote_grouped_launch(VoteArgs a, int ref_count) {
+    a.queue_cap = vote_grouped_queue_cap(a.chunk_rows);
+    if (const char *e = getenv("PPF_B200_VOTE_QUEUE")) {          // test hook: force the queue-overflow path
+        const int v = atoi(e) / 1024 * 1024;
+        if (v >= 2 * (int)kGTile && v <= a.queue_cap) a.queue_cap = v;
+    }
+    // one CTA per reference point reuses one hit collection for every chunk; with few reference points the
+    // chunks are split over several CTAs to keep all SMs busy (and the tail short)
+    int splits = 1;
+    if (const char *e = getenv("PPF_B200_VOTE_SPLITS")) splits = atoi(e);
+    else if (ref_count > 0) splits = (148 * 8 + ref_count - 1) / ref_count;
+    a.n_splits = std::max(1, std::min(splits, a.n_chunks));
+    const long long grid = (long long)ref_count * a.n_splits;
+    if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, split) CTAs"); return PPF_ERR_UNSUPPORTED; }
+    const size_t smem = vote_grouped_smem(a.chunk_rows);
+    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vote_kernel_grouped<1024><<<(unsigned)grid, 1024, smem>>>(a);
+    count_launch();
+    return PPF_OK;
+}
+
+}  // namespace ppf

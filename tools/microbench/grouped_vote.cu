@@ -1,0 +1,113 @@
+// Microbenchmark for the grouped vote loop: a warp processes HG hits of the same
+// bucket x (32/HG) staged entries per ATOMS, so that the lanes of one ATOMS mostly fall into the
+// same accumulator row (bank = (bin + row) mod 32 -> conflict-free, same cell -> merged).
+// Compares against the classical loop (32 different entries of one hit per ATOMS).
+// nvcc -O3 -gencode arch=compute_100a,code=sm_100a -o grouped_vote grouped_vote.cu
+#include <cstdio>
+#include <cstdint>
+#include <cuda_runtime.h>
+
+constexpr int ROWS = 992, S = ROWS + 1, BINS = 31;
+constexpr int STAGE = 32;                                     // entries staged per warp per block
+constexpr int BLOCKS_PER_WARP = 2048;
+
+__device__ __forceinline__ unsigned lcg(unsigned &s) { s = s * 1664525u + 1013904223u; return s; }
+__device__ __forceinline__ void red_shared(uint32_t addr) {
+    asm volatile("red.shared.add.u32 [%0], 1;" ::"r"(addr) : "memory");
+}
+
+// HG = 0: classical (lane = entry, one hit per warp pass)
+template <int HG>
+__global__ void __launch_bounds__(1024) bench(unsigned long long *cycles, unsigned *sink, int per_row) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    uint32_t *acc = reinterpret_cast<uint32_t *>(smem);
+    uint2 *stage = reinterpret_cast<uint2 *>(smem + ((BINS * S * 4 + 15) / 16 * 16)) + (threadIdx.x >> 5) * STAGE;
+    for (int i = threadIdx.x; i < BINS * S; i += blockDim.x) acc[i] = 0;
+    __syncthreads();
+    const uint32_t acc_base = (uint32_t)__cvta_generic_to_shared(acc);
+    const unsigned lane = threadIdx.x & 31;
+    unsigned s = threadIdx.x * 2654435761u + blockIdx.x * 97u + 1u;
+    uint32_t worst = 0;
+    long long t0 = clock64();
+    if constexpr (HG == 0) {
+        uint32_t hit = lcg(s) | 0xFFFu;
+        for (int b = 0; b < BLOCKS_PER_WARP / 8; b++) {       // 8 entries per lane per batch, like vote_batch<8>
+            uint32_t e[8];
+            unsigned rowbase = lcg(s) >> 12;
+#pragma unroll
+            for (int u = 0; u < 8; u++) e[u] = (lcg(s) & 0xFFFFF000u) | (((rowbase + (u * 32 + lane) / per_row)) % ROWS);
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                uint32_t d = hit - e[u];
+                unsigned long long p = (unsigned long long)d * 30ull;
+                worst = max(worst, (uint32_t)p - 0x56000u);
+                atomicAdd(&acc[(uint32_t)(p >> 32) * S + (e[u] & 0x7FFu)], 1u);
+            }
+        }
+    } else {
+        constexpr int EG = 32 / (HG ? HG : 1);                           // entries per ATOMS
+        constexpr int K = STAGE / EG;                         // consecutive staged entries per lane group
+        const unsigned g = lane / (HG ? HG : 1);
+        const uint32_t hit = lcg(s) | 0xFFFu;                 // per-lane theta_v (different hit per lane % HG)
+        for (int b = 0; b < BLOCKS_PER_WARP * HG / 32; b++) {
+            // stage: lane j writes entry j of the block (pre-decoded)
+            unsigned rowbase = __shfl_sync(0xffffffffu, lcg(s) >> 12, 0);
+            uint32_t e = lcg(s) & 0xFFFFF000u;
+            uint32_t row = (rowbase + lane / per_row) % ROWS;
+            __syncwarp();
+            stage[lane] = make_uint2(e, acc_base + row * 4);
+            __syncwarp();
+            const uint4 *src = reinterpret_cast<const uint4 *>(stage + g * K);
+#pragma unroll
+            for (int k = 0; k < K / 2; k++) {
+                uint4 q = src[k];
+                {
+                    uint32_t d = hit - q.x;
+                    unsigned long long p = (unsigned long long)d * 30ull;
+                    worst = max(worst, (uint32_t)p - 0x56000u);
+                    red_shared((uint32_t)(p >> 32) * (S * 4) + q.y);
+                }
+                {
+                    uint32_t d = hit - q.z;
+                    unsigned long long p = (unsigned long long)d * 30ull;
+                    worst = max(worst, (uint32_t)p - 0x56000u);
+                    red_shared((uint32_t)(p >> 32) * (S * 4) + q.w);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    long long t1 = clock64();
+    if (threadIdx.x == 0) cycles[blockIdx.x] = (unsigned long long)(t1 - t0);
+    unsigned x = worst;
+    for (int i = threadIdx.x; i < BINS * S; i += blockDim.x) x += acc[i];
+    if (x == 0xdeadbeef) sink[0] = x;
+}
+
+template <int HG>
+void run(const char *name, int per_row) {
+    int nsm = 148, threads = 1024;
+    unsigned *sink; unsigned long long *cyc;
+    cudaMalloc(&sink, 4); cudaMalloc(&cyc, nsm * 8);
+    size_t smem = (BINS * S * 4 + 15) / 16 * 16 + 32 * STAGE * 8;
+    cudaFuncSetAttribute(bench<HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bench<HG><<<nsm, threads, smem>>>(cyc, sink, per_row);
+    bench<HG><<<nsm, threads, smem>>>(cyc, sink, per_row);
+    cudaDeviceSynchronize();
+    unsigned long long h[148]; cudaMemcpy(h, cyc, nsm * 8, cudaMemcpyDeviceToHost);
+    double avg = 0; for (int i = 0; i < nsm; i++) avg += h[i]; avg /= nsm;
+    double votes = (double)threads * BLOCKS_PER_WARP * (HG == 0 ? 1.0 : 1.0);   // per lane: BLOCKS_PER_WARP votes
+    printf("%-28s per_row=%3d  %.3f votes/clk/SM   err=%s\n", name, per_row, votes / avg,
+           cudaGetErrorString(cudaGetLastError()));
+    cudaFree(sink); cudaFree(cyc);
+}
+
+int main() {
+    for (int per_row : {1, 4, 10, 32}) {
+        run<0>("classical (lane = entry)", per_row);
+        run<8>("grouped HG=8", per_row);
+        run<16>("grouped HG=16", per_row);
+        run<32>("grouped HG=32", per_row);
+    }
+    return 0;
+}
