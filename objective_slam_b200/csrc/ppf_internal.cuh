@@ -57,6 +57,7 @@ struct ModelTable {
     uint32_t *hashkeys = nullptr, *counts = nullptr, *first = nullptr, *map = nullptr;
     uint32_t *entries = nullptr;
     int n_chunks = 0, chunk_rows = 0;
+    int prefer_grouped = 0;                   // chunk geometry was chosen for the grouped vote kernel
     uint2 *ranges = nullptr;
     int K_d = 0;
     uint32_t *cell2bucket = nullptr;
@@ -88,6 +89,9 @@ struct VoteResult {                           // device buffers of one ppf_looku
     // [3]=overflow flag ; votes_total (u64) separately
     uint32_t *scalars = nullptr;
     unsigned long long *votes_total = nullptr;
+    // grouped vote kernel: work counters ([0] next reference point, [1 + r] next chunk of reference point r)
+    uint32_t *sched = nullptr;
+    size_t sched_cap = 0;
     // survivors, ordered (count desc, code asc) -- model.cu:155-170
     size_t K = 0;
     unsigned long long *codes = nullptr;

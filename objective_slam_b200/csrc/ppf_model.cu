@@ -353,17 +353,7 @@ int model_build(ModelTable &m) {
     }
     if (!(m.d_dist > 0.f)) { set_last_error("model: d_dist must be > 0"); return PPF_ERR_INVALID; }
     m.inv_d_dist = 1.0f / m.d_dist;
-    // the grouped vote kernel trades accumulator rows for a bigger hit queue (ppf_internal.cuh)
-    int max_rows = kGroupedMaxRows;
-    if (const char *e = getenv("PPF_B200_VOTE")) {
-        if (!strcmp(e, "classic")) max_rows = kMaxChunkRows;
-    }
-    if (const char *e = getenv("PPF_B200_CHUNK_ROWS")) {        // test hook: force more / smaller chunks
-        int v = atoi(e);
-        if (v >= 32 && v <= kMaxChunkRows) max_rows = v / 32 * 32;
-    }
-    m.n_chunks = std::max(1, (n + max_rows - 1) / max_rows);
-    m.chunk_rows = std::max(32, (((n + m.n_chunks - 1) / m.n_chunks) + 31) / 32 * 32);
+    m.n_chunks = 1; m.chunk_rows = 32;
     PPF_CUDA_TRY(cudaMalloc(&m.weights, std::max(1, n) * sizeof(float)));
     if (n > 0) fill_kernel<<<(n + 255) / 256, 256>>>(m.weights, n, 1.0f);
     count_launch();
@@ -439,6 +429,25 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(cudaMemcpyAsync(m.counts, uc, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, 0));
     PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, m.counts, m.first, m.U));
 
+    // Accumulator chunk geometry = which vote kernel serves this table.  The grouped kernel (small chunks,
+    // big hit queue: ppf_vote_grouped.cu) wins when voting dominates, i.e. when buckets are long (10k-point
+    // model: 14.7k entries per bucket on average, +17%); with short buckets (2k-point model: 800) hit
+    // collection and sorting dominate and the one-hit-per-pass kernel with 1504-row chunks is faster.
+    {
+        const double avg_bucket = (double)total / (double)std::max<uint32_t>(1u, m.U);
+        m.prefer_grouped = avg_bucket >= 5000.0;
+        if (const char *e = getenv("PPF_B200_VOTE")) {
+            if (!strcmp(e, "classic")) m.prefer_grouped = 0;
+            if (!strcmp(e, "grouped")) m.prefer_grouped = 1;
+        }
+        int max_rows = m.prefer_grouped ? kGroupedMaxRows : kMaxChunkRows;
+        if (const char *e = getenv("PPF_B200_CHUNK_ROWS")) {        // test hook: force more / smaller chunks
+            int v = atoi(e);
+            if (v >= 32 && v <= kMaxChunkRows) max_rows = v / 32 * 32;
+        }
+        m.n_chunks = std::max(1, (n + max_rows - 1) / max_rows);
+        m.chunk_rows = std::max(32, (((n + m.n_chunks - 1) / m.n_chunks) + 31) / 32 * 32);
+    }
     // vote payload in bucket order, per-chunk bucket slices, cell table
     PPF_CUDA_TRY(cudaMalloc(&m.entries, total * 4));
     gather_entries_kernel<<<grid, 256>>>(m.map, theta, total, n, m.chunk_rows, m.entries);

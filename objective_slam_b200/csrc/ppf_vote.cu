@@ -277,7 +277,7 @@ static int ensure(void **p, size_t bytes) {
 }
 
 void vote_result_free(VoteResult &r) {
-    cudaFree(r.cand_codes); cudaFree(r.cand_counts); cudaFree(r.scalars); cudaFree(r.votes_total);
+    cudaFree(r.cand_codes); cudaFree(r.cand_counts); cudaFree(r.scalars); cudaFree(r.votes_total); cudaFree(r.sched);
     cudaFree(r.codes); cudaFree(r.counts); cudaFree(r.transformations); cudaFree(r.weighted);
     cudaFree(r.trans); cudaFree(r.rots); cudaFree(r.scores);
     r.ws.release();
@@ -322,12 +322,8 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
     const int R = R_all > shard_rank ? (R_all - shard_rank + shard_count - 1) / shard_count : 0;
     if (pairs_out) *pairs_out = (unsigned long long)R * (unsigned long long)ns;
     if (launches) *launches = 0;
-    // kernel choice: the grouped kernel needs the smaller accumulator chunk the model build gives it by
-    // default (PPF_B200_VOTE=classic at build time keeps 1504-row chunks and the one-hit-per-pass kernel)
-    bool use_grouped = vote_grouped_supported(m, ns);
-    if (const char *e = getenv("PPF_B200_VOTE")) {
-        if (!strcmp(e, "classic")) use_grouped = false;
-    }
+    // kernel choice: made with the chunk geometry at model build time (ppf_model.cu)
+    const bool use_grouped = m.prefer_grouped && vote_grouped_supported(m, ns);
     for (int attempt = 0; attempt < 8; attempt++) {
         PPF_CUDA_TRY(cudaMemsetAsync(r.scalars, 0, 4 * sizeof(uint32_t), 0));
         PPF_CUDA_TRY(cudaMemsetAsync(r.votes_total, 0, 2 * sizeof(unsigned long long), 0));
@@ -345,7 +341,7 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
         a.cell2bucket = m.cell2bucket; a.ranges = m.ranges; a.entries = m.entries; a.map = m.map;
         a.n_chunks = m.n_chunks; a.chunk_rows = m.chunk_rows;
-        a.queue_cap = 0; a.n_splits = 1;
+        a.queue_cap = 0; a.n_splits = 1; a.sched = nullptr;
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;
         a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
         a.scalars = r.scalars; a.totals = r.votes_total;
@@ -353,6 +349,13 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         const long long grid = (long long)R * m.n_chunks;
         if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, chunk) CTAs"); return PPF_ERR_UNSUPPORTED; }
         if (use_grouped) {
+            if (r.sched_cap < (size_t)R + 1) {
+                cudaFree(r.sched); r.sched = nullptr; r.sched_cap = 0;
+                PPF_CUDA_TRY(cudaMalloc(&r.sched, ((size_t)R + 1) * sizeof(uint32_t)));
+                r.sched_cap = (size_t)R + 1;
+            }
+            PPF_CUDA_TRY(cudaMemsetAsync(r.sched, 0, ((size_t)R + 1) * sizeof(uint32_t), 0));
+            a.sched = r.sched;
             int rc = vote_grouped_launch(a, R);
             if (rc) return rc;
         } else if (smem > 113 * 1024) {

@@ -24,8 +24,10 @@ struct VoteArgs {
     const uint2 *ranges;
     const uint32_t *entries, *map;
     int n_chunks, chunk_rows;
-    // grouped kernel only: hit queue capacity (records) and how many CTAs share the chunks of one reference point
+    // grouped kernel only: hit queue capacity (records); work counters: sched[0] = next reference point,
+    // sched[1 + r] = next chunk of reference point r (zeroed before the launch)
     int queue_cap, n_splits;
+    uint32_t *sched;
     // output
     float thr;
     int emit_all;                                 // 1: emit every non-zero cell (vote histogram)

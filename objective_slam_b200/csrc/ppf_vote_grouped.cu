@@ -11,7 +11,7 @@
 // decoded once per hit.  Here
 //   * one CTA owns one scene reference point: ALL its hits are collected once (phase 1), sorted by
 //     bucket in shared memory (bitonic sort of 8-byte records), and reused for every model chunk;
-//   * a bucket hit h times is cut into pieces of 32 / 16 / 8 hits (+ single hits for the rest);
+//   * a bucket hit h times is cut into pieces of 32 / 16 / 8 / 4 hits (+ single hits for the rest);
 //     a warp votes HG hits x (32 / HG) entries per ATOMS: the lanes of one ATOMS fall into one or two
 //     accumulator rows (conflict-free by the row stride, equal cells merged by ATOMS.POPC.INC), an
 //     entry is fetched once per HG hits and decoded once (staged in shared memory as
@@ -55,9 +55,9 @@ bool vote_grouped_supported(const ModelTable &m, int ns) {
            vote_grouped_queue_cap(m.chunk_rows) >= 2 * (int)kGTile;
 }
 
-// piece code: 0 = single hit (classical loop), c = 1..3 -> 2^(c+2) = 8 / 16 / 32 hits
-__device__ __forceinline__ uint32_t piece_hits(uint32_t code) { return code ? (4u << code) : 1u; }
-__device__ __forceinline__ uint32_t piece_grab(uint32_t code) { return code ? (kGGrabVotes >> (code + 2)) : (uint32_t)kVoteGrab; }
+// piece code: 0 = single hit (classical loop), c = 1..4 -> 2^(c+1) = 4 / 8 / 16 / 32 hits
+__device__ __forceinline__ uint32_t piece_hits(uint32_t code) { return code ? (2u << code) : 1u; }
+__device__ __forceinline__ uint32_t piece_grab(uint32_t code) { return code ? (kGGrabVotes >> (code + 1)) : (uint32_t)kVoteGrab; }
 
 struct GroupCtx {
     const unsigned long long *queue;
@@ -65,7 +65,7 @@ struct GroupCtx {
     uint32_t trash_addr;                            // pad column of the accumulator (bin 0)
 };
 
-// One ticket of a grouped piece: HG = 4 << code hits queue[i0 .. i0 + HG) x entries [pos_grab, pos_grab + ngrab).
+// One ticket of a grouped piece: HG = 2 << code hits queue[i0 .. i0 + HG) x entries [pos_grab, pos_grab + ngrab).
 // Lane l votes for hit l % HG and belongs to entry group g = l / HG (EG = 32 / HG groups).  A block is 64
 // consecutive entries (two coalesced loads per lane); group g owns K = 2 HG of them: its position 2m holds
 // entry m EG + g and position 2m + 1 entry 32 + m EG + g, so that (a) the lane that loaded entries l and
@@ -76,7 +76,7 @@ struct GroupCtx {
 __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx &gc, const FrameYZ &FS, uint32_t i0,
                                              uint32_t code, const uint32_t *__restrict__ entries, uint32_t pos_grab,
                                              uint32_t ngrab, int lane, uint32_t &n_exact) {
-    const uint32_t lhg = code + 2u;                 // log2(HG)
+    const uint32_t lhg = code + 1u;                 // log2(HG)
     const uint32_t HG = 1u << lhg, EG = 32u >> lhg, K = 2u * HG;
     const uint32_t g = (uint32_t)lane >> lhg;
     const unsigned long long rec = gc.queue[i0 + ((uint32_t)lane & (HG - 1u))];
@@ -149,13 +149,30 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
         __syncwarp();
         const uint32_t worst0 = (hit_slow || slowmask) ? 0xFFFFFFFFu : 0u;
         if (nvalid == 64u) {
-            // sub-batches of 8 positions (4 LDS.128), one guard-band test each
-#pragma unroll 1
-            for (uint32_t p = 0; p < K; p += 8) {
-                const uint4 q0 = src[p / 2], q1 = src[p / 2 + 1], q2 = src[p / 2 + 2], q3 = src[p / 2 + 3];
+            // sub-batches of 8 positions (4 LDS.128), one guard-band test each; K = 8 (HG = 4) or a
+            // multiple of 16
+            uint32_t p = 0;
+            if (K & 8u) {
+                const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
                 uint32_t worst = worst0;
                 vote2(q0, worst); vote2(q1, worst); vote2(q2, worst); vote2(q3, worst);
-                if (worst >= kGuardSpan) repair(p, p + 8, pos_grab + blk0);
+                if (worst >= kGuardSpan) repair(0, 8, pos_grab + blk0);
+                p = 8;
+            }
+#pragma unroll 1
+            for (; p < K; p += 16) {
+                {
+                    const uint4 q0 = src[p / 2], q1 = src[p / 2 + 1], q2 = src[p / 2 + 2], q3 = src[p / 2 + 3];
+                    uint32_t worst = worst0;
+                    vote2(q0, worst); vote2(q1, worst); vote2(q2, worst); vote2(q3, worst);
+                    if (worst >= kGuardSpan) repair(p, p + 8, pos_grab + blk0);
+                }
+                {
+                    const uint4 q0 = src[p / 2 + 4], q1 = src[p / 2 + 5], q2 = src[p / 2 + 6], q3 = src[p / 2 + 7];
+                    uint32_t worst = worst0;
+                    vote2(q0, worst); vote2(q1, worst); vote2(q2, worst); vote2(q3, worst);
+                    if (worst >= kGuardSpan) repair(p + 8, p + 16, pos_grab + blk0);
+                }
             }
         } else {
             // last, partial block: the first 32 entries sit at the even positions, so pairs past
@@ -227,25 +244,13 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     __shared__ PointN s_R;
     __shared__ FrameYZ s_FS;
 
+    __shared__ int s_job, s_chunk;
+
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int split = blockIdx.x / a.ref_count;
-    const int refk = blockIdx.x - split * a.ref_count;
-    const int s_r = a.ref_start + refk * a.ref_stride;
-    const int cps = (a.n_chunks + a.n_splits - 1) / a.n_splits;
-    const int c0 = split * cps, c1 = min(a.n_chunks, c0 + cps);
-    if (c0 >= c1) return;
+    int s_r = 0, p_r = 0;                           // the job's reference point: caller's index / stored position
 
     for (int i = tid; i < kNAlphaBins * S; i += THREADS) acc[i] = 0;
     if (tid == 0) { s_exact = 0; s_votes = 0; s_nhits = 0; }
-
-    const int p_r = (int)__ldg(a.sinv + s_r);
-    if (tid == 0) {
-        float4 p = __ldg(a.spos + p_r), q = __ldg(a.snrm + p_r);
-        PointN R;
-        R.x = p.x; R.y = p.y; R.z = p.z; R.nx = q.x; R.ny = q.y; R.nz = q.z; R.nn = q.w;
-        s_R = R;
-        s_FS = load_frame(a.sfy, a.sfz, p_r);
-    }
     const FrameYZ &FS = s_FS;
     VoteCtx ctx;
     ctx.map = a.map; ctx.mfy = a.mfy; ctx.mfz = a.mfz; ctx.mpos = a.mpos; ctx.spos = a.spos;
@@ -327,8 +332,8 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                 __syncthreads();
             }
         }
-        // A bucket hit h times: h / 32 pieces of 32 hits, then 16 / 8 by the bits of the remainder, then
-        // single hits.
+        // A bucket hit h times: h / 32 pieces of 32 hits, then 16 / 8 / 4 by the bits of the remainder,
+        // then single hits.
         heads = 0;
         for (int k = 0; k < items; k++) {
             const uint32_t idx = (uint32_t)(tid * items + k);
@@ -338,13 +343,14 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             const uint32_t hi = queue_lower_bound(queue, n, (unsigned long long)(b + 1u) << kGBucketShift);
             const uint32_t h = hi - lo, o = idx - lo, full = h & ~31u;
             uint32_t hc = 0;                                       // head << 3 | code
-            if (o < full) { if ((o & 31u) == 0u) hc = 8u | 3u; }
+            if (o < full) { if ((o & 31u) == 0u) hc = 8u | 4u; }
             else {
                 const uint32_t r = h - full, q = o - full;
-                const uint32_t p16 = r & 16u, p8 = r & 8u;
-                if (p16 && q == 0u) hc = 8u | 2u;
-                else if (p8 && q == p16) hc = 8u | 1u;
-                else if (q >= p16 + p8) hc = 8u;
+                const uint32_t p16 = r & 16u, p8 = r & 8u, p4 = r & 4u;
+                if (p16 && q == 0u) hc = 8u | 3u;
+                else if (p8 && q == p16) hc = 8u | 2u;
+                else if (p4 && q == p16 + p8) hc = 8u | 1u;
+                else if (q >= p16 + p8 + p4) hc = 8u;
             }
             heads |= (unsigned long long)hc << (4 * k);
         }
@@ -419,13 +425,62 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
         __syncthreads();
     };
 
-    // ---- first pass: all hits of the reference point, whatever the chunk
-    for (uint32_t base = 0; base < (uint32_t)a.ns; base += kGTile) collect_tile(base, nullptr);
-    __syncthreads();
-    const uint32_t n_all = s_nhits;
-    const bool single = n_all <= Q;                 // the common case: one collection + one sort serve every chunk
+    // ---- jobs.  Persistent CTAs draw reference points from sched[0]; the chunks of reference point r are
+    // drawn from sched[1 + r].  When the reference points run out, an idle CTA becomes a HELPER: it picks the
+    // reference point with the most chunks left, repeats its hit collection (a few % of its work) and
+    // draws chunks from the same counter, so the heaviest reference points do not leave the other SMs idle.
+    while (true) {
+        __syncthreads();
+        if (tid == 0) s_job = (int)atomicAdd(&a.sched[0], 1u);
+        __syncthreads();
+        int job = s_job;
+        if (job >= a.ref_count) {
+            // helper: reference point with the most chunks not yet drawn (ties: spread by CTA)
+            unsigned long long best = 0;
+            for (int r = tid; r < a.ref_count; r += THREADS) {
+                const uint32_t taken = *(volatile uint32_t *)(a.sched + 1 + r);
+                if (taken < (uint32_t)a.n_chunks) {
+                    const uint32_t left = (uint32_t)a.n_chunks - taken;
+                    const uint32_t mix = ((uint32_t)r * 2654435761u + blockIdx.x * 40503u) >> 20;
+                    best = max(best, ((unsigned long long)left << 44) | ((unsigned long long)mix << 32) | (uint32_t)(r + 1));
+                }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) best = max(best, __shfl_xor_sync(0xffffffffu, best, o));
+            __syncthreads();
+            if (lane == 0) reinterpret_cast<unsigned long long *>(gend)[warp] = best;
+            __syncthreads();
+            best = 0;
+            for (int w = 0; w < THREADS / 32; w++) best = max(best, reinterpret_cast<unsigned long long *>(gend)[w]);
+            if (best == 0) break;                    // nothing left anywhere
+            job = (int)(uint32_t)best - 1;
+        }
+        s_r = a.ref_start + job * a.ref_stride;
+        p_r = (int)__ldg(a.sinv + s_r);
+        __syncthreads();
+        if (tid == 0) {
+            float4 p = __ldg(a.spos + p_r), q = __ldg(a.snrm + p_r);
+            PointN R;
+            R.x = p.x; R.y = p.y; R.z = p.z; R.nx = q.x; R.ny = q.y; R.nz = q.z; R.nn = q.w;
+            s_R = R;
+            s_FS = load_frame(a.sfy, a.sfz, p_r);
+            s_nhits = 0;
+        }
+        __syncthreads();
 
-    for (int c = c0; c < c1; c++) {
+        // ---- first pass: all hits of the reference point, whatever the chunk
+        for (uint32_t base = 0; base < (uint32_t)a.ns; base += kGTile) collect_tile(base, nullptr);
+        __syncthreads();
+        const uint32_t n_all = s_nhits;
+        const bool single = n_all <= Q;             // the common case: one collection + one sort serve every chunk
+        bool sorted = false;
+
+        while (true) {
+            __syncthreads();
+            if (tid == 0) s_chunk = (int)atomicAdd(&a.sched[1 + job], 1u);
+            __syncthreads();
+            const int c = s_chunk;
+            if (c >= a.n_chunks) break;
         const uint2 *__restrict__ ranges = a.ranges + (size_t)c * a.U;
         ctx.chunk_base = c * C;
         uint32_t base = 0;
@@ -445,7 +500,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                 n = s_nhits;
             }
             if (n) {
-                if (!single || c == c0) sort_and_cut(n);
+                if (!single || !sorted) { sort_and_cut(n); sorted = true; }
                 vote_chunk(n, ranges);
             }
             if (single || base >= (uint32_t)a.ns) break;
@@ -498,7 +553,8 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             }
         }
         __syncthreads();
-    }
+        }   // chunks of this job
+    }       // jobs
 
 #pragma unroll
     for (int o = 16; o; o >>= 1) my_exact += __shfl_xor_sync(0xffffffffu, my_exact, o);
@@ -519,14 +575,14 @@ int vote_grouped_launch(VoteArgs a, int ref_count) {
         const int v = atoi(e) / 1024 * 1024;
         if (v >= 2 * (int)kGTile && v <= a.queue_cap) a.queue_cap = v;
     }
-    // one CTA per reference point reuses one hit collection for every chunk; with few reference points the
-    // chunks are split over several CTAs to keep all SMs busy (and the tail short)
-    int splits = 1;
-    if (const char *e = getenv("PPF_B200_VOTE_SPLITS")) splits = atoi(e);
-    else if (ref_count > 0) splits = (148 * 8 + ref_count - 1) / ref_count;
-    a.n_splits = std::max(1, std::min(splits, a.n_chunks));
-    const long long grid = (long long)ref_count * a.n_splits;
-    if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, split) CTAs"); return PPF_ERR_UNSUPPORTED; }
+    // persistent CTAs (one per SM: the kernel takes all of its shared memory) draw (reference point, chunk)
+    // work from the counters in a.sched (zeroed by the caller)
+    a.n_splits = 1;
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (const char *e = getenv("PPF_B200_VOTE_CTAS")) n_sm = std::max(1, atoi(e));
+    const long long grid = n_sm;
     const size_t smem = vote_grouped_smem(a.chunk_rows);
     PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     vote_kernel_grouped<1024><<<(unsigned)grid, 1024, smem>>>(a);

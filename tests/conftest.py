@@ -13,6 +13,21 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
 
 
+def pytest_generate_tests(metafunc):
+    """Every GPU test runs against BOTH vote kernels (grouped / one-hit-per-pass): the library picks one
+    per model by bucket length, the tests force each in turn through the PPF_B200_VOTE hook."""
+    if metafunc.definition.get_closest_marker("gpu") is not None:
+        metafunc.parametrize("vote_kernel", ["grouped", "classic"], indirect=True)
+
+
+@pytest.fixture(autouse=True)
+def vote_kernel(request, monkeypatch):
+    kind = getattr(request, "param", None)
+    if kind in ("grouped", "classic"):
+        monkeypatch.setenv("PPF_B200_VOTE", kind)
+    yield kind
+
+
 def _make(target_dir, *args):
     subprocess.run(["make", "-C", os.path.join(ROOT, target_dir), *args], check=True, capture_output=True)
 

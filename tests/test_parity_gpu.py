@@ -95,6 +95,15 @@ def test_model_split_into_several_chunks(monkeypatch):
     compare_all(mp, mn, sp, sn, d, 2)
 
 
+def test_hit_queue_overflow(monkeypatch):
+    """Grouped kernel: a reference point with more hits than the shared-memory queue holds re-collects its
+    hits chunk by chunk (queue forced down to 4096 records; 6000-point scene, 3 model chunks)."""
+    monkeypatch.setenv("PPF_B200_VOTE_QUEUE", "4096")
+    monkeypatch.setenv("PPF_B200_CHUNK_ROWS", "256")
+    mp, mn, sp, sn, d, _ = clouds(600, 6000, 0.08, seed=12)
+    compare_all(mp, mn, sp, sn, d, 40)
+
+
 @pytest.mark.parametrize("l1,avg,thr", [(True, False, 0.4), (False, True, 0.4), (False, False, 0.9), (False, False, 0.0)])
 def test_lookup_options(l1, avg, thr):
     mp, mn, sp, sn, d, _ = clouds(250, 400, 0.06, seed=21)
