@@ -283,6 +283,11 @@ def main():
         achieved = votes_per_launch * 4 / (launch_ms * 1e-3) / 1e9
         tpv = ncu_traffic_bytes_per_vote()
         err_t = float(np.linalg.norm(res.pose[:3, 3].astype(np.float64) - T[:3, 3]))
+        grouped = model.layout()[2]
+        kernel_name = "ppf::vote_kernel_grouped" if grouped else "ppf::vote_kernel"
+        # ceiling of the accumulate step: ATOMS issue rate measured by the microbenchmark.  The grouped kernel's
+        # ATOMS are conflict-free by construction (1.11 wavefronts each), the classic kernel's hit random banks.
+        atoms_per_clk, atoms_kind = (17.8, "conflict-free") if grouped else (12.15, "random cell")
         line = {
             "metric": "scene point-pairs voted/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -299,17 +304,20 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"kernel": "ppf::vote_kernel", "bound": "hbm", "achieved": achieved, "peak": peak,
+            "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
                          "algorithmic_bytes_per_vote": 4, "votes_per_launch": votes_per_launch,
                          "launch_ms": launch_ms,
                          "traffic": (tpv * votes_per_launch) if tpv is not None else None,
-                         "note": "entries are mostly served from L2 (see profiles/): the binding limit is "
-                                 "shared-memory atomic issue, reported in roofline_atomic"},
+                         "note": "algorithmic traffic = one 4-byte bucket entry per vote (SURVEY 8d); the kernel "
+                                 "fetches an entry once per group of hits and mostly from L2 (measured DRAM bytes in "
+                                 "`traffic`), so frac > 1 is expected: the binding limits are the shared-memory "
+                                 "atomic / L1TEX data pipe and instruction issue, reported in roofline_atomic"},
             "roofline_atomic": {"bound": "smem-atomic issue", "achieved": votes_per_launch / (launch_ms * 1e-3),
-                                "peak": 12.15 * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None,
+                                "peak": atoms_per_clk * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None,
                                 "unit": "votes/s",
-                                "peak_source": "tools/microbench/smem_atomics.cu: 12.15 ATOMS/clk/SM (random cell) x 148 SMs x SM clock under load"},
+                                "peak_source": f"tools/microbench/smem_atomics.cu: {atoms_per_clk} ATOMS/clk/SM "
+                                               f"({atoms_kind}) x 148 SMs x SM clock under load"},
         }
         if line["roofline_atomic"]["peak"]:
             line["roofline_atomic"]["frac"] = line["roofline_atomic"]["achieved"] / line["roofline_atomic"]["peak"]

@@ -85,6 +85,14 @@ int ppf_model_create(const float *xyz, int xyz_stride, const float *nrm, int nrm
                      int use_averaged_clusters, ppf_model_t **out);
 void ppf_model_destroy(ppf_model_t *model);
 int ppf_model_num_points(const ppf_model_t *model);
+/* Persistent model database (the reference rebuilds the table for every (scene, model) pair,
+ * ppf.cu:63-70): the built table -- cloud, frames, ParallelHashArray arrays, vote payload, cell table, options --
+ * in one little-endian file.  A loaded model is indistinguishable from the one that was saved. */
+int ppf_model_save(const ppf_model_t *model, const char *path);
+int ppf_model_load(const char *path, ppf_model_t **out);
+/* How the table is laid out for voting: accumulator chunks, model points per chunk, and which vote kernel serves
+ * it (1 = grouped, ppf_vote_grouped.cu; 0 = one hit per warp pass, ppf_vote.cu).  Any output may be NULL. */
+int ppf_model_layout(const ppf_model_t *model, int *n_chunks, int *chunk_rows, int *grouped_kernel);
 
 /* ParallelHashArray contents: U unique sorted keys, counts, first index, and the
  * N*N-long key-ordered map of pair indices (m_r*N + m_i).  size_t-typed like the

@@ -56,6 +56,12 @@ class Model {                      // model.h:14-115
                                vote_count_threshold, use_l1_norm, use_averaged_clusters, &h_));
         check(ppf_lookup_create(&lk_));
     }
+    // persistent model database (no reference equivalent: ppf.cu:63-70 rebuilds the table per pair)
+    Model(const char *path, bool cpu_clustering = false) : cpu_clustering(cpu_clustering) {
+        check(ppf_model_load(path, &h_));
+        check(ppf_lookup_create(&lk_));
+    }
+    void save(const char *path) const { check(ppf_model_save(h_, path)); }
     ~Model() { ppf_lookup_destroy(lk_); ppf_model_destroy(h_); }
     Model(const Model &) = delete;
     Model &operator=(const Model &) = delete;

@@ -19,7 +19,8 @@ PPF_MEM_HOST, PPF_MEM_DEVICE = 0, 1
 EXPORTS = [
     "ppf_last_error", "ppf_version", "ppf_kernel_launch_count",
     "ppf_scene_create", "ppf_scene_destroy", "ppf_scene_num_points", "ppf_scene_features",
-    "ppf_model_create", "ppf_model_destroy", "ppf_model_num_points", "ppf_model_table_sizes",
+    "ppf_model_create", "ppf_model_destroy", "ppf_model_num_points", "ppf_model_save", "ppf_model_load",
+    "ppf_model_layout", "ppf_model_table_sizes",
     "ppf_model_table_get", "ppf_model_features", "ppf_point_pair_feature", "ppf_trans_model_scene", "ppf_voxel_grid",
     "ppf_lookup_create", "ppf_lookup_destroy", "ppf_model_lookup", "ppf_lookup_vote",
     "ppf_lookup_local_max", "ppf_lookup_finalize", "ppf_lookup_survivors", "ppf_lookup_set_survivors",
@@ -79,6 +80,9 @@ def _load():
     L.ppf_model_destroy.argtypes = [vp]
     L.ppf_model_destroy.restype = None
     L.ppf_model_num_points.argtypes = [vp]
+    L.ppf_model_save.argtypes = [vp, ctypes.c_char_p]
+    L.ppf_model_load.argtypes = [ctypes.c_char_p, P(vp)]
+    L.ppf_model_layout.argtypes = [vp, P(ci), P(ci), P(ci)]
     L.ppf_model_table_sizes.argtypes = [vp, P(sz), P(sz)]
     L.ppf_model_table_get.argtypes = [vp, vp, vp, vp, vp]
     L.ppf_model_features.argtypes = [vp, ci, ci, ci, ci, vp, vp]

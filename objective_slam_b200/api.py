@@ -19,6 +19,7 @@ in the CUDA library.  Clouds may be numpy arrays (host) or torch CUDA tensors (d
 from __future__ import annotations
 
 import ctypes
+import os
 from dataclasses import dataclass
 
 import numpy as np
@@ -169,6 +170,30 @@ class Model:
         self.vote_count_threshold = float(vote_count_threshold)
         self.cpu_clustering = bool(cpu_clustering)
         self._lookup = None
+
+    # -- persistent model database ------------------------------
+    def save(self, path: str):
+        """Write the built table to `path` (ppf_model_save)."""
+        C.check(C.lib.ppf_model_save(self._h, os.fsencode(path)))
+
+    @classmethod
+    def load(cls, path: str, cpu_clustering: bool = False) -> "Model":
+        """Model handle from a file written by save(): no rebuild (ppf_model_load)."""
+        self = cls.__new__(cls)
+        self._h = ctypes.c_void_p()
+        C.check(C.lib.ppf_model_load(os.fsencode(path), ctypes.byref(self._h)))
+        self.n = int(C.lib.ppf_model_num_points(self._h))
+        self.d_dist = None
+        self.vote_count_threshold = None
+        self.cpu_clustering = bool(cpu_clustering)
+        self._lookup = None
+        return self
+
+    def layout(self):
+        """(n_chunks, chunk_rows, grouped_kernel): how the table is laid out for voting."""
+        a, b, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        C.check(C.lib.ppf_model_layout(self._h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+        return a.value, b.value, bool(c.value)
 
     # -- model_description -------------------------------------------------------
     def table(self):

@@ -103,6 +103,27 @@ void ppf_model_destroy(ppf_model_t *m) {
 }
 int ppf_model_num_points(const ppf_model_t *m) { return m ? m->table.cloud.n : 0; }
 
+int ppf_model_save(const ppf_model_t *m, const char *path) {
+    PPF_CHECK_ARG(m && path, "model save: NULL argument");
+    return model_save(m->table, path);
+}
+int ppf_model_load(const char *path, ppf_model_t **out) {
+    PPF_CHECK_ARG(out && path, "model load: NULL argument");
+    *out = nullptr;
+    ppf_model *m = new ppf_model();
+    int rc = model_load(m->table, path);
+    if (rc) { model_free(m->table); delete m; return rc; }
+    *out = m;
+    return PPF_OK;
+}
+int ppf_model_layout(const ppf_model_t *m, int *n_chunks, int *chunk_rows, int *grouped_kernel) {
+    PPF_CHECK_ARG(m, "model is NULL");
+    if (n_chunks) *n_chunks = m->table.n_chunks;
+    if (chunk_rows) *chunk_rows = m->table.chunk_rows;
+    if (grouped_kernel) *grouped_kernel = m->table.prefer_grouped;
+    return PPF_OK;
+}
+
 int ppf_model_table_sizes(const ppf_model_t *m, size_t *U, size_t *npairs) {
     PPF_CHECK_ARG(m, "model is NULL");
     if (U) *U = m->table.U;

@@ -126,6 +126,8 @@ int  features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, in
                    float *ppfs_host, uint32_t *keys_host);
 int  model_build(ModelTable &m);
 void model_free(ModelTable &m);
+int  model_save(const ModelTable &m, const char *path);
+int  model_load(ModelTable &m, const char *path);
 int  model_table_get(const ModelTable &m, uint32_t *hashkeys, size_t *counts, size_t *first, size_t *map);
 int  vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_rank, int shard_count,
               int emit_all, VoteResult &r, unsigned long long *pairs_out, int *launches);

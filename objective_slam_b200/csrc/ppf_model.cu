@@ -11,6 +11,7 @@
 //  * the vote payload (chunk-local m_r, alpha_m as a 19-bit binary angle) is
 //    gathered into bucket order once, so voting streams 4 B per vote.
 #include <cub/cub.cuh>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -471,6 +472,100 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(cudaDeviceSynchronize());
     return PPF_OK;
+}
+
+// ---- persistent model database (no reference equivalent: ppf.cu:63-70 rebuilds the table for
+// every (scene, model) pair).  One little-endian file: header, then every device array of the table verbatim.
+namespace {
+struct ModelFileHeader {
+    char magic[8];                     // "PPFB200\0"
+    uint32_t version, n, U, K_d;
+    int32_t n_chunks, chunk_rows, prefer_grouped, use_l1_norm, use_averaged_clusters;
+    float d_dist, vote_count_threshold;
+    uint32_t reserved[5];
+};
+constexpr uint32_t kModelFileVersion = 2;
+constexpr size_t kIoChunk = (size_t)32 << 20;
+
+int dev_to_file(FILE *f, const void *dev, size_t bytes, std::vector<char> &buf) {
+    for (size_t off = 0; off < bytes; off += kIoChunk) {
+        const size_t n = std::min(kIoChunk, bytes - off);
+        PPF_CUDA_TRY(cudaMemcpy(buf.data(), (const char *)dev + off, n, cudaMemcpyDeviceToHost));
+        if (fwrite(buf.data(), 1, n, f) != n) { set_last_error("model save: short write"); return PPF_ERR_INVALID; }
+    }
+    return PPF_OK;
+}
+int file_to_dev(FILE *f, void **dev, size_t bytes, std::vector<char> &buf) {
+    PPF_CUDA_TRY(cudaMalloc(dev, std::max<size_t>(bytes, 16)));
+    for (size_t off = 0; off < bytes; off += kIoChunk) {
+        const size_t n = std::min(kIoChunk, bytes - off);
+        if (fread(buf.data(), 1, n, f) != n) { set_last_error("model load: file truncated"); return PPF_ERR_INVALID; }
+        PPF_CUDA_TRY(cudaMemcpy((char *)*dev + off, buf.data(), n, cudaMemcpyHostToDevice));
+    }
+    return PPF_OK;
+}
+struct ArraySpec { void **ptr; size_t bytes; };
+std::vector<ArraySpec> model_arrays(ModelTable &m) {
+    const size_t n = std::max(1, m.cloud.n), total = (size_t)m.cloud.n * m.cloud.n;
+    const bool tiny = m.cloud.n <= 1;
+    const size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
+    return {
+        {(void **)&m.cloud.pos, n * sizeof(float4)}, {(void **)&m.cloud.nrm, n * sizeof(float4)},
+        {(void **)&m.cloud.fy, n * sizeof(float4)},  {(void **)&m.cloud.fz, n * sizeof(float4)},
+        {(void **)&m.weights, n * sizeof(float)},
+        {(void **)&m.hashkeys, tiny ? 4 : (size_t)m.U * 4}, {(void **)&m.counts, tiny ? 4 : (size_t)m.U * 4},
+        {(void **)&m.first, tiny ? 4 : (size_t)m.U * 4},
+        {(void **)&m.map, tiny ? 4 : total * 4}, {(void **)&m.entries, tiny ? 4 : total * 4},
+        {(void **)&m.ranges, tiny ? 8 : (size_t)m.U * m.n_chunks * sizeof(uint2)},
+        {(void **)&m.cell2bucket, tiny ? 4 : ncell * 4},
+    };
+}
+}  // namespace
+
+int model_save(const ModelTable &mc, const char *path) {
+    ModelTable &m = const_cast<ModelTable &>(mc);          // model_arrays only reads the pointers here
+    FILE *f = fopen(path, "wb");
+    if (!f) { set_last_error(std::string("model save: cannot open ") + path); return PPF_ERR_INVALID; }
+    ModelFileHeader h{};
+    memcpy(h.magic, "PPFB200", 8);
+    h.version = kModelFileVersion; h.n = (uint32_t)m.cloud.n; h.U = m.U; h.K_d = (uint32_t)m.K_d;
+    h.n_chunks = m.n_chunks; h.chunk_rows = m.chunk_rows; h.prefer_grouped = m.prefer_grouped;
+    h.use_l1_norm = m.use_l1_norm; h.use_averaged_clusters = m.use_averaged_clusters;
+    h.d_dist = m.d_dist; h.vote_count_threshold = m.vote_count_threshold;
+    int rc = fwrite(&h, sizeof(h), 1, f) == 1 ? PPF_OK : PPF_ERR_INVALID;
+    std::vector<char> buf(kIoChunk);
+    for (auto &a : model_arrays(m)) {
+        if (rc) break;
+        rc = dev_to_file(f, *a.ptr, a.bytes, buf);
+    }
+    if (fclose(f) != 0 && !rc) { set_last_error("model save: close failed"); rc = PPF_ERR_INVALID; }
+    return rc;
+}
+
+int model_load(ModelTable &m, const char *path) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { set_last_error(std::string("model load: cannot open ") + path); return PPF_ERR_INVALID; }
+    ModelFileHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, "PPFB200", 8) != 0 || h.version != kModelFileVersion ||
+        h.n > (uint32_t)PPF_MAX_MODEL_POINTS || h.n_chunks < 1 || h.chunk_rows < 32 || h.chunk_rows > kMaxChunkRows ||
+        (long long)h.n_chunks * h.chunk_rows < (long long)h.n || !(h.d_dist > 0.f) || h.K_d > 65536u ||
+        (h.n > 1 && (h.U == 0 || (size_t)h.U > (size_t)h.n * h.n)) || (h.prefer_grouped && h.chunk_rows > kGroupedMaxRows)) {
+        fclose(f);
+        set_last_error("model load: not a ppf_b200 model file of this version (or corrupt header)");
+        return PPF_ERR_INVALID;
+    }
+    m.cloud.n = (int)h.n; m.U = h.U; m.K_d = (int)h.K_d; m.n_chunks = h.n_chunks; m.chunk_rows = h.chunk_rows;
+    m.prefer_grouped = h.prefer_grouped; m.use_l1_norm = h.use_l1_norm; m.use_averaged_clusters = h.use_averaged_clusters;
+    m.d_dist = h.d_dist; m.inv_d_dist = 1.0f / h.d_dist; m.vote_count_threshold = h.vote_count_threshold;
+    std::vector<char> buf(kIoChunk);
+    int rc = PPF_OK;
+    for (auto &a : model_arrays(m)) {
+        if (rc) break;
+        rc = file_to_dev(f, a.ptr, a.bytes, buf);
+    }
+    if (!rc && fgetc(f) != EOF) { set_last_error("model load: trailing bytes"); rc = PPF_ERR_INVALID; }
+    fclose(f);
+    return rc;
 }
 
 int model_table_get(const ModelTable &m, uint32_t *hashkeys, size_t *counts, size_t *first, size_t *map) {

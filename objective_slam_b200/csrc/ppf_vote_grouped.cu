@@ -313,7 +313,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
         for (uint32_t k = 2; k <= P; k <<= 1) {
             const uint32_t hk = k >> 1;
             for (uint32_t t = tid; t < P / 2; t += THREADS) {
-                const uint32_t blk = (t / hk) * k, o = t & (hk - 1u);
+                const uint32_t blk = (t & ~(hk - 1u)) << 1, o = t & (hk - 1u);      // (t / hk) * k
                 const uint32_t i = blk + o, l = blk + k - 1u - o;
                 if (l < n) {
                     const unsigned long long x = queue[i], y = queue[l];

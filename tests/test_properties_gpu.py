@@ -141,3 +141,30 @@ def test_config5_dense_million_point_scene():
         votes += lk.stats().num_nonunique_votes
     assert votes == whole.num_nonunique_votes
     assert (whole.votes >> np.uint64(32)).max() < 1_000_000
+
+
+def test_saved_model_is_the_built_model(tmp_path):
+    """a model table written by ppf_model_save and read back by ppf_model_load gives the
+    same hash arrays, the same layout and bit-identical lookup results as the table that was built."""
+    import objective_slam_b200 as ppf
+    from objective_slam_b200 import synth
+    mp, mn = synth.make_model(700, seed=31)
+    sp, sn, _ = synth.make_scene(mp, mn, 1500, seed=32)
+    d = synth.d_dist_for(mp)
+    built = ppf.Model(mp, mn, d)
+    path = str(tmp_path / "model.ppfb200")
+    built.save(path)
+    loaded = ppf.Model.load(path)
+    assert loaded.n == built.n and loaded.layout() == built.layout()
+    for a, b in zip(built.table(), loaded.table()):
+        assert (a == b).all()
+    s = ppf.Scene(sp, sn, d, 3)
+    r0, r1 = built.ppf_lookup(s), loaded.ppf_lookup(s)
+    assert r0.num_nonunique_votes == r1.num_nonunique_votes and r0.num_top_votes == r1.num_top_votes
+    assert (r0.votes == r1.votes).all() and (r0.voteCounts == r1.voteCounts).all()
+    assert (r0.pose.view(np.uint32) == r1.pose.view(np.uint32)).all()
+    # a truncated file is refused, not read
+    blob = open(path, "rb").read()
+    open(path, "wb").write(blob[: len(blob) // 2])
+    with pytest.raises(ppf.PpfError):
+        ppf.Model.load(path)
