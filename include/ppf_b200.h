@@ -62,6 +62,9 @@ const char *ppf_last_error(void);
 const char *ppf_version(void);
 /* Number of kernels of this library launched by the process so far (diagnostic; bench.py's gpu_launches). */
 uint64_t ppf_kernel_launch_count(void);
+/* Destroyed scenes / models park their device block in a small cache (<= 16 blocks, <= 6 GB) so that a
+ * recognition loop does not call cudaMalloc / cudaFree per frame; this returns the cached blocks to the driver. */
+void ppf_release_cached_memory(void);
 
 /* ---- Scene ------------------------------------------------------------------ */
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n,

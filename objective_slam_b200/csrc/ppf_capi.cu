@@ -54,6 +54,7 @@ extern "C" {
 const char *ppf_last_error(void) { return g_last_error.c_str(); }
 const char *ppf_version(void) { return "ppf_b200 0.1 (sm_100a)"; }
 uint64_t ppf_kernel_launch_count(void) { return g_kernel_launches.load(); }
+void ppf_release_cached_memory(void) { pool_trim(); }
 
 // ---- Scene ------------------------------------------------------------------------
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem,

@@ -46,6 +46,8 @@ struct Cloud {
     // reference point than any model pair is long.  order[p] = caller's index of stored point p,
     // inv[i] = stored position of the caller's point i (nullptr for model clouds: identity).
     uint32_t *order = nullptr, *inv = nullptr;
+    char *block = nullptr;                             // the one device allocation all arrays above / below live in
+    size_t block_cap = 0;                              // (nullptr for a cloud read by model_load)
     float4 *gbox_lo = nullptr, *gbox_hi = nullptr;     // AABB of every 32-point group
     float4 *tbox_lo = nullptr, *tbox_hi = nullptr;     // AABB of every kHitQueue-point tile
 };
@@ -56,6 +58,7 @@ struct ModelTable {
     uint32_t U = 0;                           // unique keys
     uint32_t *hashkeys = nullptr, *counts = nullptr, *first = nullptr, *map = nullptr;
     uint32_t *entries = nullptr;
+    size_t map_cap = 0, entries_cap = 0;      // != 0: the array is a block of the device block cache
     int n_chunks = 0, chunk_rows = 0;
     int prefer_grouped = 0;                   // chunk geometry was chosen for the grouped vote kernel
     uint2 *ranges = nullptr;
@@ -104,6 +107,14 @@ struct VoteResult {                           // device buffers of one ppf_looku
     uint32_t max_idx = 0;
     size_t cap_K = 0;
 };
+
+// cache of device blocks of destroyed clouds (ppf_model.cu): no cudaMalloc / cudaFree per Scene in steady state
+void *pool_alloc(size_t bytes, size_t *cap_out);
+void  pool_free(void *p, size_t cap);
+void  pool_trim();
+cudaError_t pooled_malloc_bytes(void **p, size_t bytes);
+void  pooled_free(void *p);
+template <typename T> inline cudaError_t pooled_malloc(T **p, size_t bytes) { return pooled_malloc_bytes((void **)p, bytes); }
 
 // error plumbing (never exit(): SURVEY 8b "Errors")
 void set_last_error(const std::string &msg);

@@ -12,6 +12,8 @@
 //    gathered into bucket order once, so voting streams 4 B per vote.
 #include <cub/cub.cuh>
 #include <cstdio>
+#include <mutex>
+#include <unordered_map>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -40,9 +42,96 @@ __global__ void pack_cloud_kernel(const float *__restrict__ xyz, int xs, const f
     fz[p] = make_float4(f.z[0], f.z[1], f.z[2], f.z[3]);
 }
 
+// ---- device block cache ------------------------------------------------------------------------------
+// A recognition loop creates and destroys one Scene per frame (ppf.cu:56-99).  cudaMalloc / cudaFree
+// synchronise the device and were measured at 1-800 ms per Scene on a B200 box under load, so a cloud lives
+// in ONE device block and destroyed clouds park their block here for the next cloud of similar size.
+namespace {
+struct CachedBlock { void *ptr; size_t cap; int device; };
+std::mutex g_pool_mutex;
+std::vector<CachedBlock> g_pool;
+constexpr size_t kPoolMaxBlocks = 64;
+constexpr size_t kPoolMaxBytes = (size_t)6 << 30;
+}  // namespace
+
+void *pool_alloc(size_t bytes, size_t *cap_out) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        size_t best = g_pool.size();
+        for (size_t i = 0; i < g_pool.size(); i++)
+            if (g_pool[i].device == dev && g_pool[i].cap >= bytes && g_pool[i].cap <= 2 * bytes + (1u << 20) &&
+                (best == g_pool.size() || g_pool[i].cap < g_pool[best].cap))
+                best = i;
+        if (best != g_pool.size()) {
+            void *p = g_pool[best].ptr;
+            *cap_out = g_pool[best].cap;
+            g_pool.erase(g_pool.begin() + best);
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaMalloc(&p, bytes) != cudaSuccess) {
+        pool_trim();                                  // give the cached blocks back and try once more
+        if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
+    }
+    *cap_out = bytes;
+    return p;
+}
+void pool_free(void *p, size_t cap) {
+    if (!p) return;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        size_t total = cap;
+        for (auto &b : g_pool) total += b.cap;
+        if (g_pool.size() < kPoolMaxBlocks && total <= kPoolMaxBytes) {
+            g_pool.push_back({p, cap, dev});
+            return;
+        }
+    }
+    cudaFree(p);
+}
+void pool_trim() {
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    for (auto &b : g_pool) cudaFree(b.ptr);
+    g_pool.clear();
+}
+
+// cudaMalloc / cudaFree look-alikes on top of the block cache (the capacity of every live block is remembered)
+namespace {
+std::unordered_map<void *, size_t> g_live_caps;
+}
+cudaError_t pooled_malloc_bytes(void **p, size_t bytes) {
+    size_t cap = 0;
+    *p = pool_alloc(bytes ? bytes : 16, &cap);
+    if (!*p) return cudaErrorMemoryAllocation;
+    std::lock_guard<std::mutex> lock(g_pool_mutex);
+    g_live_caps[*p] = cap;
+    return cudaSuccess;
+}
+void pooled_free(void *p) {
+    if (!p) return;
+    size_t cap = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        auto it = g_live_caps.find(p);
+        if (it == g_live_caps.end()) { cudaFree(p); return; }      // not ours (cannot happen)
+        cap = it->second;
+        g_live_caps.erase(it);
+    }
+    pool_free(p, cap);
+}
+
 void cloud_free(Cloud &c) {
-    cudaFree(c.pos); cudaFree(c.nrm); cudaFree(c.fy); cudaFree(c.fz);
-    cudaFree(c.order); cudaFree(c.inv); cudaFree(c.gbox_lo); cudaFree(c.gbox_hi); cudaFree(c.tbox_lo); cudaFree(c.tbox_hi);
+    if (c.block) {
+        pool_free(c.block, c.block_cap);              // every array of the cloud lives in the block
+    } else {                                          // a cloud read by model_load: one allocation per array
+        pooled_free(c.pos); pooled_free(c.nrm); pooled_free(c.fy); pooled_free(c.fz);
+        pooled_free(c.order); pooled_free(c.inv); pooled_free(c.gbox_lo); pooled_free(c.gbox_hi); pooled_free(c.tbox_lo); pooled_free(c.tbox_hi);
+    }
     c = Cloud();
 }
 
@@ -107,20 +196,23 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
         return PPF_ERR_INVALID;
     }
     c.n = n;
-    size_t nn = n > 0 ? (size_t)n : 1;
-    PPF_CUDA_TRY(cudaMalloc(&c.pos, nn * sizeof(float4)));
-    PPF_CUDA_TRY(cudaMalloc(&c.nrm, nn * sizeof(float4)));
-    PPF_CUDA_TRY(cudaMalloc(&c.fy, nn * sizeof(float4)));
-    PPF_CUDA_TRY(cudaMalloc(&c.fz, nn * sizeof(float4)));
-    if (n == 0) return PPF_OK;
-    Workspace ws;
-    struct Release { Workspace &w; ~Release() { w.release(); } } rel{ws};
-    size_t bx = ((size_t)(n - 1) * xs + 3) * sizeof(float), bn = ((size_t)(n - 1) * ns + 3) * sizeof(float);
+    const size_t nn = n > 0 ? (size_t)n : 1;
+    const int ng = (n + 31) / 32, nt = (n + kHitQueue - 1) / kHitQueue;
+    const size_t bx = n > 0 ? ((size_t)(n - 1) * xs + 3) * sizeof(float) : 0, bn = n > 0 ? ((size_t)(n - 1) * ns + 3) * sizeof(float) : 0;
     size_t sort_tmp = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                    (uint32_t *)nullptr, n);
-    int rc = ws.reserve((mem == PPF_MEM_HOST ? bx + bn : 0) + (spatial_sort ? (size_t)n * 12 + sort_tmp + 64 : 0) + 64);
-    if (rc) return rc;
+    if (n > 0)
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                        (uint32_t *)nullptr, n);
+    // one block: the cloud's arrays, then the scratch of this function (host staging, Morton keys, CUB storage)
+    const size_t persistent = 4 * nn * sizeof(float4) + (spatial_sort ? 2 * nn * 4 + 2 * (size_t)(ng + nt + 2) * sizeof(float4) : 0);
+    const size_t scratch = (mem == PPF_MEM_HOST ? bx + bn : 0) + (spatial_sort ? nn * 12 + sort_tmp + 64 : 0);
+    const size_t want = persistent + scratch + 32 * 256;
+    c.block = (char *)pool_alloc(want, &c.block_cap);
+    if (!c.block) { set_last_error("cloud: out of device memory"); return PPF_ERR_CUDA; }
+    Workspace ws;                                      // bump allocator over the block (does not own it)
+    ws.base = c.block; ws.cap = c.block_cap; ws.used = 0;
+    c.pos = ws.take<float4>(nn); c.nrm = ws.take<float4>(nn); c.fy = ws.take<float4>(nn); c.fz = ws.take<float4>(nn);
+    if (n == 0) return PPF_OK;
     const float *dx = xyz, *dn = nrm;
     if (mem == PPF_MEM_HOST) {
         float *tx = (float *)ws.take_bytes(bx), *tn = (float *)ws.take_bytes(bn);
@@ -133,8 +225,7 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
         float *mm = ws.take<float>(6);
         uint32_t *key = ws.take<uint32_t>(n), *key_s = ws.take<uint32_t>(n), *idx = ws.take<uint32_t>(n);
         void *tmp = ws.take_bytes(sort_tmp);
-        PPF_CUDA_TRY(cudaMalloc(&c.order, (size_t)n * 4));
-        PPF_CUDA_TRY(cudaMalloc(&c.inv, (size_t)n * 4));
+        c.order = ws.take<uint32_t>(n); c.inv = ws.take<uint32_t>(n);
         const float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
         PPF_CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, 0));
         bbox_kernel<<<grid, 256>>>(dx, xs, n, mm);
@@ -149,11 +240,9 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     if (spatial_sort) {
-        const int ng = (n + 31) / 32, nt = (n + kHitQueue - 1) / kHitQueue;
-        PPF_CUDA_TRY(cudaMalloc(&c.gbox_lo, (size_t)ng * sizeof(float4)));
-        PPF_CUDA_TRY(cudaMalloc(&c.gbox_hi, (size_t)ng * sizeof(float4)));
-        PPF_CUDA_TRY(cudaMalloc(&c.tbox_lo, (size_t)nt * sizeof(float4)));
-        PPF_CUDA_TRY(cudaMalloc(&c.tbox_hi, (size_t)nt * sizeof(float4)));
+        c.gbox_lo = ws.take<float4>(ng); c.gbox_hi = ws.take<float4>(ng);
+        c.tbox_lo = ws.take<float4>(nt); c.tbox_hi = ws.take<float4>(nt);
+        if (!c.gbox_lo || !c.gbox_hi || !c.tbox_lo || !c.tbox_hi) { set_last_error("cloud: block too small"); return PPF_ERR_CUDA; }
         boxes_kernel<<<std::min((ng + 127) / 128, 148 * 8), 128>>>(c.pos, n, 32, c.gbox_lo, c.gbox_hi, ng);
         count_launch();
         boxes_kernel<<<std::min((nt + 127) / 128, 148 * 8), 128>>>(c.pos, n, kHitQueue, c.tbox_lo, c.tbox_hi, nt);
@@ -216,15 +305,15 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
     size_t total = (size_t)(re - rb) * (size_t)(oe - ob);
     if (total == 0) return PPF_OK;
     float4 *dp = nullptr; uint32_t *dk = nullptr;
-    if (ppfs_host) PPF_CUDA_TRY(cudaMalloc(&dp, total * sizeof(float4)));
-    if (keys_host) PPF_CUDA_TRY(cudaMalloc(&dk, total * sizeof(uint32_t)));
+    if (ppfs_host) PPF_CUDA_TRY(pooled_malloc(&dp, total * sizeof(float4)));
+    if (keys_host) PPF_CUDA_TRY(pooled_malloc(&dk, total * sizeof(uint32_t)));
     int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
     features_tile_kernel<<<blocks, 256>>>(c.pos, c.nrm, c.inv, c.n, d_dist, 1.0f / d_dist, df, rb, re, ob, oe, dp, dk);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     if (dp) PPF_CUDA_TRY(cudaMemcpy(ppfs_host, dp, total * sizeof(float4), cudaMemcpyDeviceToHost));
     if (dk) PPF_CUDA_TRY(cudaMemcpy(keys_host, dk, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    cudaFree(dp); cudaFree(dk);
+    pooled_free(dp); pooled_free(dk);
     return PPF_OK;
 }
 
@@ -341,8 +430,10 @@ __global__ void fill_kernel(float *v, int n, float x) {
 
 void model_free(ModelTable &m) {
     cloud_free(m.cloud);
-    cudaFree(m.hashkeys); cudaFree(m.counts); cudaFree(m.first); cudaFree(m.map);
-    cudaFree(m.entries); cudaFree(m.ranges); cudaFree(m.cell2bucket); cudaFree(m.weights);
+    pooled_free(m.hashkeys); pooled_free(m.counts); pooled_free(m.first);
+    if (m.map_cap) pool_free(m.map, m.map_cap); else pooled_free(m.map);
+    if (m.entries_cap) pool_free(m.entries, m.entries_cap); else pooled_free(m.entries);
+    pooled_free(m.ranges); pooled_free(m.cell2bucket); pooled_free(m.weights);
     m = ModelTable();
 }
 
@@ -355,7 +446,7 @@ int model_build(ModelTable &m) {
     if (!(m.d_dist > 0.f)) { set_last_error("model: d_dist must be > 0"); return PPF_ERR_INVALID; }
     m.inv_d_dist = 1.0f / m.d_dist;
     m.n_chunks = 1; m.chunk_rows = 32;
-    PPF_CUDA_TRY(cudaMalloc(&m.weights, std::max(1, n) * sizeof(float)));
+    PPF_CUDA_TRY(pooled_malloc(&m.weights, std::max(1, n) * sizeof(float)));
     if (n > 0) fill_kernel<<<(n + 255) / 256, 256>>>(m.weights, n, 1.0f);
     count_launch();
     // Every reference kernel returns early when count <= 1 (kernel.cu:406,461): a model with
@@ -364,10 +455,10 @@ int model_build(ModelTable &m) {
     if (n <= 1) {
         m.U = (uint32_t)total;              // n==1: one key (0); n==0: none
         m.K_d = 0;
-        PPF_CUDA_TRY(cudaMalloc(&m.hashkeys, 4)); PPF_CUDA_TRY(cudaMalloc(&m.counts, 4));
-        PPF_CUDA_TRY(cudaMalloc(&m.first, 4)); PPF_CUDA_TRY(cudaMalloc(&m.map, 4));
-        PPF_CUDA_TRY(cudaMalloc(&m.entries, 4)); PPF_CUDA_TRY(cudaMalloc(&m.ranges, 8));
-        PPF_CUDA_TRY(cudaMalloc(&m.cell2bucket, 4));
+        PPF_CUDA_TRY(pooled_malloc(&m.hashkeys, 4)); PPF_CUDA_TRY(pooled_malloc(&m.counts, 4));
+        PPF_CUDA_TRY(pooled_malloc(&m.first, 4)); PPF_CUDA_TRY(pooled_malloc(&m.map, 4));
+        PPF_CUDA_TRY(pooled_malloc(&m.entries, 4)); PPF_CUDA_TRY(pooled_malloc(&m.ranges, 8));
+        PPF_CUDA_TRY(pooled_malloc(&m.cell2bucket, 4));
         uint32_t z = 0, one = 1;
         cudaMemcpy(m.hashkeys, &z, 4, cudaMemcpyHostToDevice);
         cudaMemcpy(m.counts, &one, 4, cudaMemcpyHostToDevice);
@@ -406,7 +497,8 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(cudaGetLastError());
 
     // sort (key, pair index): LSD radix sort, stable, so every bucket ascends in pair index
-    PPF_CUDA_TRY(cudaMalloc(&m.map, total * 4));
+    m.map = (uint32_t *)pool_alloc(total * 4, &m.map_cap);      // the two N^2 arrays come from the block cache
+    if (!m.map) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
     iota_kernel<<<grid, 256>>>(iota, total);
     count_launch();
     PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, keys, keys_sorted, iota, m.map, total));
@@ -423,9 +515,9 @@ int model_build(ModelTable &m) {
         return PPF_ERR_UNSUPPORTED;
     }
     m.K_d = h_maxkd + 1;
-    PPF_CUDA_TRY(cudaMalloc(&m.hashkeys, (size_t)m.U * 4));
-    PPF_CUDA_TRY(cudaMalloc(&m.counts, (size_t)m.U * 4));
-    PPF_CUDA_TRY(cudaMalloc(&m.first, (size_t)m.U * 4));
+    PPF_CUDA_TRY(pooled_malloc(&m.hashkeys, (size_t)m.U * 4));
+    PPF_CUDA_TRY(pooled_malloc(&m.counts, (size_t)m.U * 4));
+    PPF_CUDA_TRY(pooled_malloc(&m.first, (size_t)m.U * 4));
     PPF_CUDA_TRY(cudaMemcpyAsync(m.hashkeys, uk, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, 0));
     PPF_CUDA_TRY(cudaMemcpyAsync(m.counts, uc, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, 0));
     PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, m.counts, m.first, m.U));
@@ -450,11 +542,12 @@ int model_build(ModelTable &m) {
         m.chunk_rows = std::max(32, (((n + m.n_chunks - 1) / m.n_chunks) + 31) / 32 * 32);
     }
     // vote payload in bucket order, per-chunk bucket slices, cell table
-    PPF_CUDA_TRY(cudaMalloc(&m.entries, total * 4));
+    m.entries = (uint32_t *)pool_alloc(total * 4, &m.entries_cap);
+    if (!m.entries) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
     gather_entries_kernel<<<grid, 256>>>(m.map, theta, total, n, m.chunk_rows, m.entries);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
-    PPF_CUDA_TRY(cudaMalloc(&m.ranges, (size_t)m.U * m.n_chunks * sizeof(uint2)));
+    PPF_CUDA_TRY(pooled_malloc(&m.ranges, (size_t)m.U * m.n_chunks * sizeof(uint2)));
     {
         size_t t = (size_t)m.U * m.n_chunks;
         chunk_ranges_kernel<<<(int)std::min<size_t>((t + 255) / 256, 148 * 32), 256>>>(
@@ -463,7 +556,7 @@ int model_build(ModelTable &m) {
     }
     PPF_CUDA_TRY(cudaGetLastError());
     size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
-    PPF_CUDA_TRY(cudaMalloc(&m.cell2bucket, ncell * 4));
+    PPF_CUDA_TRY(pooled_malloc(&m.cell2bucket, ncell * 4));
     if (m.K_d > 0) {
         cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256>>>(m.hashkeys, m.U, m.K_d,
                                                                                        m.d_dist, m.cell2bucket);
@@ -496,7 +589,7 @@ int dev_to_file(FILE *f, const void *dev, size_t bytes, std::vector<char> &buf) 
     return PPF_OK;
 }
 int file_to_dev(FILE *f, void **dev, size_t bytes, std::vector<char> &buf) {
-    PPF_CUDA_TRY(cudaMalloc(dev, std::max<size_t>(bytes, 16)));
+    PPF_CUDA_TRY(pooled_malloc(dev, std::max<size_t>(bytes, 16)));
     for (size_t off = 0; off < bytes; off += kIoChunk) {
         const size_t n = std::min(kIoChunk, bytes - off);
         if (fread(buf.data(), 1, n, f) != n) { set_last_error("model load: file truncated"); return PPF_ERR_INVALID; }

@@ -275,9 +275,9 @@ __global__ void trans_model_scene_kernel(const float *m_r, const float *n_r_m, c
 // host arrays in, host arrays out (debug / operator-level API; not a hot path)
 struct DevBuf {
     void *p = nullptr;
-    ~DevBuf() { cudaFree(p); }
+    ~DevBuf() { pooled_free(p); }
     int up(const void *h, size_t bytes) {
-        if (cudaMalloc(&p, bytes ? bytes : 4) != cudaSuccess) return PPF_ERR_CUDA;
+        if (pooled_malloc(&p, bytes ? bytes : 4) != cudaSuccess) return PPF_ERR_CUDA;
         if (h && bytes && cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return PPF_ERR_CUDA;
         return PPF_OK;
     }

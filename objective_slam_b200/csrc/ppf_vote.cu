@@ -255,11 +255,12 @@ int Workspace::reserve(size_t bytes) {
     bytes += 16 * 256;                                     // alignment slack for up to 16 slices
     used = 0;
     if (bytes <= cap) return PPF_OK;
-    if (base) cudaFree(base);
+    if (base) pool_free(base, cap);
     base = nullptr; cap = 0;
-    size_t want = bytes + bytes / 2;
-    if (cudaMalloc(&base, want) != cudaSuccess) { set_last_error("workspace: out of device memory"); return PPF_ERR_CUDA; }
-    cap = want;
+    size_t want = bytes + bytes / 2, got = 0;
+    base = (char *)pool_alloc(want, &got);
+    if (!base) { set_last_error("workspace: out of device memory"); return PPF_ERR_CUDA; }
+    cap = got;
     return PPF_OK;
 }
 void *Workspace::take_bytes(size_t bytes) {
@@ -268,18 +269,18 @@ void *Workspace::take_bytes(size_t bytes) {
     used = off + bytes;
     return base + off;
 }
-void Workspace::release() { if (base) cudaFree(base); base = nullptr; cap = used = 0; }
+void Workspace::release() { if (base) pool_free(base, cap); base = nullptr; cap = used = 0; }
 
 static int ensure(void **p, size_t bytes) {
-    if (*p) cudaFree(*p);
+    if (*p) pooled_free(*p);
     *p = nullptr;
-    return cudaMalloc(p, bytes ? bytes : 16) == cudaSuccess ? PPF_OK : PPF_ERR_CUDA;
+    return pooled_malloc(p, bytes ? bytes : 16) == cudaSuccess ? PPF_OK : PPF_ERR_CUDA;
 }
 
 void vote_result_free(VoteResult &r) {
-    cudaFree(r.cand_codes); cudaFree(r.cand_counts); cudaFree(r.scalars); cudaFree(r.votes_total); cudaFree(r.sched);
-    cudaFree(r.codes); cudaFree(r.counts); cudaFree(r.transformations); cudaFree(r.weighted);
-    cudaFree(r.trans); cudaFree(r.rots); cudaFree(r.scores);
+    pooled_free(r.cand_codes); pooled_free(r.cand_counts); pooled_free(r.scalars); pooled_free(r.votes_total); pooled_free(r.sched);
+    pooled_free(r.codes); pooled_free(r.counts); pooled_free(r.transformations); pooled_free(r.weighted);
+    pooled_free(r.trans); pooled_free(r.rots); pooled_free(r.scores);
     r.ws.release();
     r = VoteResult();
 }
@@ -306,13 +307,13 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         return PPF_ERR_INVALID;
     }
     if (!r.scalars) {
-        PPF_CUDA_TRY(cudaMalloc(&r.scalars, 4 * sizeof(uint32_t)));
-        PPF_CUDA_TRY(cudaMalloc(&r.votes_total, 2 * sizeof(unsigned long long)));
+        PPF_CUDA_TRY(pooled_malloc(&r.scalars, 4 * sizeof(uint32_t)));
+        PPF_CUDA_TRY(pooled_malloc(&r.votes_total, 2 * sizeof(unsigned long long)));
     }
     if (!r.cand_codes) {
         r.cand_cap = emit_all ? (size_t)1 << 24 : (size_t)1 << 22;
-        PPF_CUDA_TRY(cudaMalloc(&r.cand_codes, r.cand_cap * 8));
-        PPF_CUDA_TRY(cudaMalloc(&r.cand_counts, r.cand_cap * 4));
+        PPF_CUDA_TRY(pooled_malloc(&r.cand_codes, r.cand_cap * 8));
+        PPF_CUDA_TRY(pooled_malloc(&r.cand_counts, r.cand_cap * 4));
     }
     r.K = 0;
     const int ns = scene.n;
@@ -350,8 +351,8 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, chunk) CTAs"); return PPF_ERR_UNSUPPORTED; }
         if (use_grouped) {
             if (r.sched_cap < (size_t)R + 1) {
-                cudaFree(r.sched); r.sched = nullptr; r.sched_cap = 0;
-                PPF_CUDA_TRY(cudaMalloc(&r.sched, ((size_t)R + 1) * sizeof(uint32_t)));
+                pooled_free(r.sched); r.sched = nullptr; r.sched_cap = 0;
+                PPF_CUDA_TRY(pooled_malloc(&r.sched, ((size_t)R + 1) * sizeof(uint32_t)));
                 r.sched_cap = (size_t)R + 1;
             }
             PPF_CUDA_TRY(cudaMemsetAsync(r.sched, 0, ((size_t)R + 1) * sizeof(uint32_t), 0));
@@ -374,10 +375,10 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         if (h[0] <= r.cand_cap) return PPF_OK;
         // candidate buffer too small: grow and vote again (results are deterministic)
         r.cand_cap = (size_t)h[0] + (h[0] >> 2) + 1024;
-        cudaFree(r.cand_codes); cudaFree(r.cand_counts);
+        pooled_free(r.cand_codes); pooled_free(r.cand_counts);
         r.cand_codes = nullptr; r.cand_counts = nullptr;
-        PPF_CUDA_TRY(cudaMalloc(&r.cand_codes, r.cand_cap * 8));
-        PPF_CUDA_TRY(cudaMalloc(&r.cand_counts, r.cand_cap * 4));
+        PPF_CUDA_TRY(pooled_malloc(&r.cand_codes, r.cand_cap * 8));
+        PPF_CUDA_TRY(pooled_malloc(&r.cand_counts, r.cand_cap * 4));
     }
     set_last_error("vote: candidate buffer kept overflowing");
     return PPF_ERR_CUDA;
