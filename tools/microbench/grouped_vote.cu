@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *cycles, unsign
         constexpr int K = STAGE / EG;                         // consecutive staged entries per lane group
         const unsigned g = lane / (HG ? HG : 1);
         const uint32_t hit = lcg(s) | 0xFFFu;                 // per-lane theta_v (different hit per lane % HG)
-        for (int b = 0; b < BLOCKS_PER_WARP * HG / 32; b++) {
+        for (int b = 0; b < BLOCKS_PER_WARP / K; b++) {           // K votes per lane and block: BLOCKS_PER_WARP votes per lane in all
             // stage: lane j writes entry j of the block (pre-decoded)
             unsigned rowbase = __shfl_sync(0xffffffffu, lcg(s) >> 12, 0);
             uint32_t e = lcg(s) & 0xFFFFF000u;
@@ -96,7 +96,7 @@ void run(const char *name, int per_row) {
     cudaDeviceSynchronize();
     unsigned long long h[148]; cudaMemcpy(h, cyc, nsm * 8, cudaMemcpyDeviceToHost);
     double avg = 0; for (int i = 0; i < nsm; i++) avg += h[i]; avg /= nsm;
-    double votes = (double)threads * BLOCKS_PER_WARP * (HG == 0 ? 1.0 : 1.0);   // per lane: BLOCKS_PER_WARP votes
+    double votes = (double)threads * BLOCKS_PER_WARP;      // every mode casts BLOCKS_PER_WARP votes per lane
     printf("%-28s per_row=%3d  %.3f votes/clk/SM   err=%s\n", name, per_row, votes / avg,
            cudaGetErrorString(cudaGetLastError()));
     cudaFree(sink); cudaFree(cyc);
