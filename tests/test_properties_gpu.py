@@ -168,3 +168,25 @@ def test_saved_model_is_the_built_model(tmp_path):
     open(path, "wb").write(blob[: len(blob) // 2])
     with pytest.raises(ppf.PpfError):
         ppf.Model.load(path)
+
+
+def test_config2_both_vote_kernels_agree_at_full_size(monkeypatch):
+    """BASELINE configs[1] at full size (10k-point model table, 50k-point scene; every 25th scene point a
+    reference point): the grouped kernel and the one-hit-per-pass kernel cast the same 4.8e11 votes into the same
+    cells -- vote total, non-zero cells, maximum, every survivor and its count, and the final pose are equal."""
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, T = _case(10000, 50000, seed=2)
+    out = {}
+    for kind in ("grouped", "classic"):
+        monkeypatch.setenv("PPF_B200_VOTE", kind)
+        m = ppf.Model(mp, mn, d)
+        assert m.layout()[2] == (kind == "grouped")
+        out[kind] = m.ppf_lookup(ppf.Scene(sp, sn, d, 25))
+        m.close()
+    a, b = out["grouped"], out["classic"]
+    assert a.num_nonunique_votes == b.num_nonunique_votes > 4e11
+    assert (a.num_unique_votes, a.max_vote_count, a.num_top_votes) == (b.num_unique_votes, b.max_vote_count, b.num_top_votes)
+    assert (a.votes == b.votes).all() and (a.voteCounts == b.voteCounts).all()
+    assert (a.pose.view(np.uint32) == b.pose.view(np.uint32)).all()
+    dt, ang = _ht_dist(a.pose.astype(np.float64), T)
+    assert dt < 0.1 * 100.0 and ang < np.radians(12), (dt, ang)
