@@ -124,6 +124,23 @@ def lookup(mpts, mnrm, spts, snrm, d_dist, ref_df=1, thr=0.4, use_l1_norm=False,
     return out
 
 
+def drost_m(mpts, mnrm, spts, snrm, d_dist=0.0, skip=5, max_refs=0, threads=0, scene_stride=1):
+    """oracle/drost_m.c: the MATLAB pipeline (model_description.m + voting_scheme.m, double precision).
+    Returns dict(seconds, build_seconds, pairs, votes, pose[4,4] float64).  Timing baseline, parity unpinned."""
+    L = lib()
+    vp, ci, cd = ctypes.c_void_p, ctypes.c_int, ctypes.c_double
+    L.drost_m_run.restype = cd
+    L.drost_m_run.argtypes = [vp, vp, ci, vp, vp, ci, cd, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_uint64),
+                              ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(cd), vp]
+    mpts, mnrm, spts, snrm = _f32(mpts), _f32(mnrm), _f32(spts), _f32(snrm)
+    pairs, votes, build_s = ctypes.c_uint64(), ctypes.c_uint64(), cd()
+    pose = np.zeros((4, 4), np.float64)
+    s = L.drost_m_run(_p(mpts), _p(mnrm), len(mpts), _p(spts), _p(snrm), len(spts), float(d_dist), int(skip),
+                      int(max_refs), int(scene_stride), int(threads), ctypes.byref(pairs), ctypes.byref(votes),
+                      ctypes.byref(build_s), pose.ctypes.data)
+    return dict(seconds=s, build_seconds=build_s.value, pairs=pairs.value, votes=votes.value, pose=pose)
+
+
 def time_voting(mpts, mnrm, spts, snrm, d_dist, ref_df=1, max_refs=0, threads=0, scene_stride=1):
     """Seconds spent voting over (up to max_refs) reference points; returns dict."""
     mpts, mnrm, spts, snrm = _f32(mpts), _f32(mnrm), _f32(spts), _f32(snrm)
