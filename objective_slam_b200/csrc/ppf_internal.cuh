@@ -95,6 +95,8 @@ struct VoteResult {                           // device buffers of one ppf_looku
     // grouped vote kernel: work counters ([0] next reference point, [1 + r] next chunk of reference point r)
     uint32_t *sched = nullptr;
     size_t sched_cap = 0;
+    uint32_t *acc_scratch = nullptr;          // accumulators of a dense scene's segments (ppf_vote_grouped.cu)
+    size_t acc_scratch_cap = 0;
     // survivors, ordered (count desc, code asc) -- model.cu:155-170
     size_t K = 0;
     unsigned long long *codes = nullptr;

@@ -278,7 +278,7 @@ static int ensure(void **p, size_t bytes) {
 }
 
 void vote_result_free(VoteResult &r) {
-    pooled_free(r.cand_codes); pooled_free(r.cand_counts); pooled_free(r.scalars); pooled_free(r.votes_total); pooled_free(r.sched);
+    pooled_free(r.cand_codes); pooled_free(r.cand_counts); pooled_free(r.scalars); pooled_free(r.votes_total); pooled_free(r.sched); pooled_free(r.acc_scratch);
     pooled_free(r.codes); pooled_free(r.counts); pooled_free(r.transformations); pooled_free(r.weighted);
     pooled_free(r.trans); pooled_free(r.rots); pooled_free(r.scores);
     r.ws.release();
@@ -342,7 +342,7 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
         a.cell2bucket = m.cell2bucket; a.ranges = m.ranges; a.entries = m.entries; a.map = m.map;
         a.n_chunks = m.n_chunks; a.chunk_rows = m.chunk_rows;
-        a.queue_cap = 0; a.n_splits = 1; a.sched = nullptr;
+        a.queue_cap = 0; a.n_splits = 1; a.sched = nullptr; a.acc_scratch = nullptr;
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;
         a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
         a.scalars = r.scalars; a.totals = r.votes_total;
@@ -350,13 +350,23 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         const long long grid = (long long)R * m.n_chunks;
         if (grid > 0x7FFFFFFFLL) { set_last_error("vote: too many (reference point, chunk) CTAs"); return PPF_ERR_UNSUPPORTED; }
         if (use_grouped) {
-            if (r.sched_cap < (size_t)R + 1) {
+            // [0] next reference point, [1, R] next chunk of each, [R + 1] dense reference points registered,
+            // [R + 2, 2R + 1] their list, [2R + 2] next of them to process
+            const size_t sched_words = 2 * (size_t)R + 3;
+            if (r.sched_cap < sched_words) {
                 pooled_free(r.sched); r.sched = nullptr; r.sched_cap = 0;
-                PPF_CUDA_TRY(pooled_malloc(&r.sched, ((size_t)R + 1) * sizeof(uint32_t)));
-                r.sched_cap = (size_t)R + 1;
+                PPF_CUDA_TRY(pooled_malloc(&r.sched, sched_words * sizeof(uint32_t)));
+                r.sched_cap = sched_words;
             }
-            PPF_CUDA_TRY(cudaMemsetAsync(r.sched, 0, ((size_t)R + 1) * sizeof(uint32_t), 0));
+            PPF_CUDA_TRY(cudaMemsetAsync(r.sched, 0, sched_words * sizeof(uint32_t), 0));
             a.sched = r.sched;
+            const size_t words = vote_grouped_scratch_words(m);
+            if (r.acc_scratch_cap < words) {
+                pooled_free(r.acc_scratch); r.acc_scratch = nullptr; r.acc_scratch_cap = 0;
+                PPF_CUDA_TRY(pooled_malloc(&r.acc_scratch, words * sizeof(uint32_t)));
+                r.acc_scratch_cap = words;
+            }
+            a.acc_scratch = r.acc_scratch;
             int rc = vote_grouped_launch(a, R);
             if (rc) return rc;
         } else if (smem > 113 * 1024) {

@@ -28,6 +28,7 @@ struct VoteArgs {
     // sched[1 + r] = next chunk of reference point r (zeroed before the launch)
     int queue_cap, n_splits;
     uint32_t *sched;
+    uint32_t *acc_scratch;                        // [CTAs][n_chunks][31 x S]: accumulators parked between scene segments
     // output
     float thr;
     int emit_all;                                 // 1: emit every non-zero cell (vote histogram)
@@ -203,5 +204,7 @@ __device__ __forceinline__ float box_dist2(const PointN &R, float4 lo, float4 hi
 // grouped kernel (ppf_vote_grouped.cu)
 bool   vote_grouped_supported(const ModelTable &m, int ns);
 int    vote_grouped_launch(VoteArgs a, int ref_count);
+int    vote_grouped_ctas();
+size_t vote_grouped_scratch_words(const ModelTable &m);
 
 }  // namespace ppf

@@ -17,8 +17,9 @@
 //     entry is fetched once per HG hits and decoded once (staged in shared memory as
 //     (entry, row address)), and a vote costs 5 instructions (IADD, IMAD.WIDE, VIADDMNMX, IMAD, ATOMS)
 //     + half an LDS.128;
-//   * the accumulator chunk is small (<= 480 model points x 31 bins) so that the queue holds 13,312
-//     hits; a reference point with more hits than that falls back to re-collecting its hits per chunk.
+//   * the accumulator chunk is small (<= 480 model points x 31 bins) so that the queue holds ~12,000 hits; a
+//     reference point with more hits than that (dense scenes) is handed to a second instantiation of the
+//     kernel that cuts the scene into segments and parks the chunk accumulators in global scratch between them.
 // tools/microbench/grouped_vote.cu: 14.2 / 11-13 / 9-11 votes/clk/SM at HG = 32 / 16 / 8 against 6.1 for
 // the classical loop inside the full kernel.
 #include <algorithm>
@@ -227,7 +228,14 @@ __device__ __forceinline__ uint32_t queue_lower_bound(const unsigned long long *
     return lo;
 }
 
-template <int THREADS>
+// SEGMENTS = false: the normal kernel (one hit collection per reference point).  A reference point with more
+// hits than the queue holds (dense scenes) is only REGISTERED there (sched[R + 2 ...]) and is processed by the
+// SEGMENTS = true instantiation, launched right after: the scene is cut into segments of tiles whose hits fit
+// the queue; every segment is collected and sorted once and voted against ALL chunks, the accumulator of a
+// chunk waiting in global scratch between two segments (60 KB per chunk and segment each way: noise next to
+// the votes).  Two instantiations keep the segment bookkeeping out of the normal kernel's registers
+// (one kernel with both paths: 104 bytes of spills, -6% on configs[1]).
+template <int THREADS, bool SEGMENTS>
 __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = a.chunk_rows, S = acc_stride(C);
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     __syncthreads();
 
     // ---- phase 1 for one tile of scene points: pairs (s_r, s_i) -> hit queue (tile / warp culling as in
-    // vote_kernel).  flt != nullptr keeps only hits whose bucket has entries in that chunk.
+    // vote_kernel).  flt != nullptr would keep only hits whose bucket has entries in that chunk (unused now).
     auto collect_tile = [&](uint32_t base, const uint2 *__restrict__ flt) {
         const PointN R = s_R;
         const FrameYZ FS = s_FS;
@@ -429,11 +437,22 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     // drawn from sched[1 + r].  When the reference points run out, an idle CTA becomes a HELPER: it picks the
     // reference point with the most chunks left, repeats its hit collection (a few % of its work) and
     // draws chunks from the same counter, so the heaviest reference points do not leave the other SMs idle.
+    uint32_t *const overflow = a.sched + 1 + a.ref_count;      // [0] = count, [1 ...] = jobs, [1 + R] = next to process
     while (true) {
         __syncthreads();
+        int job;
+        if constexpr (SEGMENTS) {
+            if (tid == 0) {
+                const uint32_t k = atomicAdd(&overflow[1 + a.ref_count], 1u);
+                s_job = k < *(volatile uint32_t *)&overflow[0] ? (int)overflow[1 + k] : -1;
+            }
+            __syncthreads();
+            job = s_job;
+            if (job < 0) break;
+        } else {
         if (tid == 0) s_job = (int)atomicAdd(&a.sched[0], 1u);
         __syncthreads();
-        int job = s_job;
+        job = s_job;
         if (job >= a.ref_count) {
             // helper: reference point with the most chunks not yet drawn (ties: spread by CTA)
             unsigned long long best = 0;
@@ -455,6 +474,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             if (best == 0) break;                    // nothing left anywhere
             job = (int)(uint32_t)best - 1;
         }
+        }
         s_r = a.ref_start + job * a.ref_stride;
         p_r = (int)__ldg(a.sinv + s_r);
         __syncthreads();
@@ -468,43 +488,69 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
         }
         __syncthreads();
 
-        // ---- first pass: all hits of the reference point, whatever the chunk
-        for (uint32_t base = 0; base < (uint32_t)a.ns; base += kGTile) collect_tile(base, nullptr);
-        __syncthreads();
-        const uint32_t n_all = s_nhits;
-        const bool single = n_all <= Q;             // the common case: one collection + one sort serve every chunk
+        uint32_t n = 0;
+        int c = -1;
         bool sorted = false;
+        // SEGMENTS only:
+        bool more_segments = false;
+        uint32_t base = 0;
+        int seg = -1;
+        if constexpr (!SEGMENTS) {
+            // ---- first pass: all hits of the reference point, whatever the chunk
+            for (uint32_t base0 = 0; base0 < (uint32_t)a.ns; base0 += kGTile) collect_tile(base0, nullptr);
+            __syncthreads();
+            n = s_nhits;
+            if (n > Q) {
+                // does not fit: claim every chunk (helpers must not touch it) and leave it to the segment kernel
+                if (tid == 0 && atomicCAS(&a.sched[1 + job], 0u, (uint32_t)a.n_chunks) == 0u)
+                    overflow[1 + atomicAdd(&overflow[0], 1u)] = (uint32_t)job;
+                continue;
+            }
+        }
 
         while (true) {
-            __syncthreads();
-            if (tid == 0) s_chunk = (int)atomicAdd(&a.sched[1 + job], 1u);
-            __syncthreads();
-            const int c = s_chunk;
-            if (c >= a.n_chunks) break;
-        const uint2 *__restrict__ ranges = a.ranges + (size_t)c * a.U;
-        ctx.chunk_base = c * C;
-        uint32_t base = 0;
-        while (true) {
-            uint32_t n = n_all;
-            if (!single) {
-                // more hits than the queue holds: collect the hits of THIS chunk tile by tile and vote
-                // whenever the queue cannot take another tile
+            if constexpr (!SEGMENTS) {
                 __syncthreads();
-                if (tid == 0) s_nhits = 0;
+                if (tid == 0) s_chunk = (int)atomicAdd(&a.sched[1 + job], 1u);
                 __syncthreads();
-                while (base < (uint32_t)a.ns && s_nhits + kGTile <= Q) {
-                    collect_tile(base, ranges);
-                    base += kGTile;
+                c = s_chunk;
+                if (c >= a.n_chunks) break;
+                if (!sorted && n) { sort_and_cut(n); sorted = true; }
+            } else {
+                if (c < 0 || c == a.n_chunks - 1) {
+                    if (c >= 0 && !more_segments) break;            // the last segment has met every chunk
+                    seg++; c = 0;
                     __syncthreads();
+                    if (tid == 0) s_nhits = 0;
+                    __syncthreads();
+                    while (base < (uint32_t)a.ns && s_nhits + kGTile <= Q) {
+                        collect_tile(base, nullptr);
+                        base += kGTile;
+                        __syncthreads();
+                    }
+                    n = s_nhits;
+                    more_segments = base < (uint32_t)a.ns;
+                    if (n) sort_and_cut(n);
+                } else {
+                    c++;
                 }
-                n = s_nhits;
+                if (seg > 0) {
+                    const uint32_t *src = a.acc_scratch + ((size_t)blockIdx.x * a.n_chunks + c) * ((size_t)kNAlphaBins * S);
+                    for (int i = tid; i < kNAlphaBins * S; i += THREADS) acc[i] = src[i];
+                }
+                __syncthreads();
             }
-            if (n) {
-                if (!single || !sorted) { sort_and_cut(n); sorted = true; }
-                vote_chunk(n, ranges);
+            const uint2 *__restrict__ ranges = a.ranges + (size_t)c * a.U;
+            ctx.chunk_base = c * C;
+            if (n) vote_chunk(n, ranges);
+            __syncthreads();
+            if constexpr (SEGMENTS) {
+                if (more_segments) {
+                    uint32_t *dst = a.acc_scratch + ((size_t)blockIdx.x * a.n_chunks + c) * ((size_t)kNAlphaBins * S);
+                    for (int i = tid; i < kNAlphaBins * S; i += THREADS) { dst[i] = acc[i]; acc[i] = 0; }
+                    continue;
+                }
             }
-            if (single || base >= (uint32_t)a.ns) break;
-        }
         __syncthreads();
         // ---- phase 3 for this chunk: block max, statistics, emission of candidate cells, reset.
         // (the pad column is scratch: partial blocks vote into it)
@@ -569,6 +615,17 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     }
 }
 
+int vote_grouped_ctas() {
+    int n_sm = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    if (const char *e = getenv("PPF_B200_VOTE_CTAS")) n_sm = std::max(1, atoi(e));
+    return n_sm;
+}
+size_t vote_grouped_scratch_words(const ModelTable &m) {
+    return (size_t)vote_grouped_ctas() * m.n_chunks * ((size_t)kNAlphaBins * acc_stride(m.chunk_rows));
+}
+
 int vote_grouped_launch(VoteArgs a, int ref_count) {
     a.queue_cap = vote_grouped_queue_cap(a.chunk_rows);
     if (const char *e = getenv("PPF_B200_VOTE_QUEUE")) {          // test hook: force the queue-overflow path
@@ -578,15 +635,14 @@ int vote_grouped_launch(VoteArgs a, int ref_count) {
     // persistent CTAs (one per SM: the kernel takes all of its shared memory) draw (reference point, chunk)
     // work from the counters in a.sched (zeroed by the caller)
     a.n_splits = 1;
-    int n_sm = 148, dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    if (const char *e = getenv("PPF_B200_VOTE_CTAS")) n_sm = std::max(1, atoi(e));
-    const long long grid = n_sm;
+    const long long grid = vote_grouped_ctas();
     const size_t smem = vote_grouped_smem(a.chunk_rows);
-    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vote_kernel_grouped<1024><<<(unsigned)grid, 1024, smem>>>(a);
-    count_launch();
+    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vote_kernel_grouped<1024, false><<<(unsigned)grid, 1024, smem>>>(a);
+    // reference points whose hits did not fit the queue (none on sparse scenes: the kernel then exits at once)
+    vote_kernel_grouped<1024, true><<<(unsigned)grid, 1024, smem>>>(a);
+    count_launch(2);
     return PPF_OK;
 }
 
