@@ -65,6 +65,11 @@ uint64_t ppf_kernel_launch_count(void);
 /* Destroyed scenes / models park their device block in a small cache (<= 16 blocks, <= 6 GB) so that a
  * recognition loop does not call cudaMalloc / cudaFree per frame; this returns the cached blocks to the driver. */
 void ppf_release_cached_memory(void);
+/* Optional hint for ppf_model_create: how many points the scenes have that the next models will be matched against
+ * (0 = unknown, the default).  It only selects the layout of the table / the vote kernel (scenes of >= 40k
+ * points favour the grouped kernel even for small models); results never depend on it.  ppf_registration sets
+ * it from its own scene list. */
+void ppf_set_expected_scene_points(int n);
 
 /* ---- Scene ------------------------------------------------------------------ */
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n,

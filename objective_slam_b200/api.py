@@ -160,11 +160,18 @@ class Model:
     """Model::Model (model.cu:43-82): uploads the cloud and builds the PPF hash table."""
 
     def __init__(self, points, normals, d_dist: float, vote_count_threshold: float = 0.4,
-                 cpu_clustering: bool = False, use_l1_norm: bool = False, use_averaged_clusters: bool = False):
+                 cpu_clustering: bool = False, use_l1_norm: bool = False, use_averaged_clusters: bool = False,
+                 expected_scene_points: int = 0):
+        """expected_scene_points (optional, not in the reference): size of the scenes this model will meet;
+        it only selects the table layout / vote kernel (ppf_set_expected_scene_points), never the results."""
         xp, xs, np_, ns, n, mem, keep = _as_cloud_arrays(points, normals)
         self._h = ctypes.c_void_p()
-        C.check(C.lib.ppf_model_create(xp, xs, np_, ns, n, mem, float(d_dist), float(vote_count_threshold),
-                                       int(use_l1_norm), int(use_averaged_clusters), ctypes.byref(self._h)))
+        C.lib.ppf_set_expected_scene_points(int(expected_scene_points))
+        try:
+            C.check(C.lib.ppf_model_create(xp, xs, np_, ns, n, mem, float(d_dist), float(vote_count_threshold),
+                                           int(use_l1_norm), int(use_averaged_clusters), ctypes.byref(self._h)))
+        finally:
+            C.lib.ppf_set_expected_scene_points(0)
         self.n = n
         self.d_dist = float(d_dist)
         self.vote_count_threshold = float(vote_count_threshold)

@@ -55,6 +55,7 @@ const char *ppf_last_error(void) { return g_last_error.c_str(); }
 const char *ppf_version(void) { return "ppf_b200 0.1 (sm_100a)"; }
 uint64_t ppf_kernel_launch_count(void) { return g_kernel_launches.load(); }
 void ppf_release_cached_memory(void) { pool_trim(); }
+void ppf_set_expected_scene_points(int n) { g_expected_scene_points.store(n > 0 ? n : 0); }
 
 // ---- Scene ------------------------------------------------------------------------
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem,
@@ -438,6 +439,12 @@ extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes,
     // the uploaded scene cloud does not depend on d_dist at all and is reused across models.
     std::vector<ppf_model_t *> models(num_models, nullptr);
     int rc = PPF_OK;
+    // the scenes are known before the model tables are laid out: tell the builder how dense they are
+    const int hint_before = g_expected_scene_points.load();
+    int largest_scene = 0;
+    for (int i = 0; i < num_scenes; i++) largest_scene = std::max(largest_scene, scene_clouds[i].n);
+    g_expected_scene_points.store(largest_scene);
+    struct RestoreHint { int v; ~RestoreHint() { g_expected_scene_points.store(v); } } restore_hint{hint_before};
     for (int j = 0; j < num_models && !rc; j++) {
         const ppf_cloud_t &c = model_clouds[j];
         rc = ppf_model_create(c.xyz, c.xyz_stride, c.nrm, c.nrm_stride, c.n, PPF_MEM_HOST, model_d_dists[j],

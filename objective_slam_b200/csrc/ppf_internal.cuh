@@ -19,6 +19,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <string>
 
 #include "ppf_math.cuh"
@@ -117,6 +118,9 @@ void  pool_trim();
 cudaError_t pooled_malloc_bytes(void **p, size_t bytes);
 void  pooled_free(void *p);
 template <typename T> inline cudaError_t pooled_malloc(T **p, size_t bytes) { return pooled_malloc_bytes((void **)p, bytes); }
+
+// size of the scenes the next models will be matched against (0 = unknown): see ppf_set_expected_scene_points
+extern std::atomic<int> g_expected_scene_points;
 
 // error plumbing (never exit(): SURVEY 8b "Errors")
 void set_last_error(const std::string &msg);

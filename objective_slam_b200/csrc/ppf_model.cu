@@ -11,6 +11,7 @@
 //  * the vote payload (chunk-local m_r, alpha_m as a 19-bit binary angle) is
 //    gathered into bucket order once, so voting streams 4 B per vote.
 #include <cub/cub.cuh>
+#include <atomic>
 #include <cstdio>
 #include <mutex>
 #include <unordered_map>
@@ -437,6 +438,9 @@ void model_free(ModelTable &m) {
     m = ModelTable();
 }
 
+std::atomic<int> g_expected_scene_points{0};
+constexpr int kDenseScenePoints = 40000;
+
 int model_build(ModelTable &m) {
     const int n = m.cloud.n;
     if (n > PPF_MAX_MODEL_POINTS) {
@@ -528,10 +532,14 @@ int model_build(ModelTable &m) {
     // collection and sorting dominate and the one-hit-per-pass kernel with 1504-row chunks is faster.
     {
         const double avg_bucket = (double)total / (double)std::max<uint32_t>(1u, m.U);
-        m.prefer_grouped = avg_bucket >= 5000.0;
+        // dense scenes (hint from the caller, ppf_set_expected_scene_points) favour the grouped kernel even with
+        // short buckets: every reference point then hits every bucket many times (2k-point model: 60k-point scene
+        // 73 ms against 103 ms, 200k 198 / 287 ms, 1M 1.36 / 1.83 s; but 16k-point scene 43 / 34 ms)
+        const bool dense_scene = g_expected_scene_points.load() >= kDenseScenePoints;
+        m.prefer_grouped = (avg_bucket >= 5000.0 || dense_scene) && m.U < (1u << 20);   // 20-bit bucket field of a hit record
         if (const char *e = getenv("PPF_B200_VOTE")) {
             if (!strcmp(e, "classic")) m.prefer_grouped = 0;
-            if (!strcmp(e, "grouped")) m.prefer_grouped = 1;
+            if (!strcmp(e, "grouped") && m.U < (1u << 20)) m.prefer_grouped = 1;
         }
         int max_rows = m.prefer_grouped ? kGroupedMaxRows : kMaxChunkRows;
         if (const char *e = getenv("PPF_B200_CHUNK_ROWS")) {        // test hook: force more / smaller chunks

@@ -190,3 +190,23 @@ def test_config2_both_vote_kernels_agree_at_full_size(monkeypatch):
     assert (a.pose.view(np.uint32) == b.pose.view(np.uint32)).all()
     dt, ang = _ht_dist(a.pose.astype(np.float64), T)
     assert dt < 0.1 * 100.0 and ang < np.radians(12), (dt, ang)
+
+
+def test_scene_size_hint_selects_the_layout_not_the_result():
+    """ppf_set_expected_scene_points: a small model meant for big scenes gets the grouped layout; the lookup
+    result is the same either way (the vote_kernel fixture is overridden by the hint only when it says auto)."""
+    import os
+    import objective_slam_b200 as ppf
+    mp, mn, sp, sn, d, _ = _case(500, 3000, seed=11)
+    forced = os.environ.pop("PPF_B200_VOTE", None)
+    try:
+        small = ppf.Model(mp, mn, d)
+        big = ppf.Model(mp, mn, d, expected_scene_points=1_000_000)
+        assert not small.layout()[2] and big.layout()[2]
+        s = ppf.Scene(sp, sn, d, 4)
+        a, b = small.ppf_lookup(s), big.ppf_lookup(s)
+        assert (a.votes == b.votes).all() and (a.voteCounts == b.voteCounts).all()
+        assert (a.pose.view(np.uint32) == b.pose.view(np.uint32)).all()
+    finally:
+        if forced is not None:
+            os.environ["PPF_B200_VOTE"] = forced
