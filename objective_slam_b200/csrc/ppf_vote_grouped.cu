@@ -85,7 +85,11 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
     const bool hit_slow = ((uint32_t)rec >> 23) & 1u;
     const uint32_t s_i = (uint32_t)rec & kGIndexMask;
     const uint32_t S4 = (uint32_t)ctx.stride * 4u;
-    const uint32_t trash = gc.trash_addr;
+    // Loop invariants that ptxas would otherwise REMATERIALISE in every block (shared-window base via S2UR +
+    // ULEA + LDC + LEA ..., lane via S2R + LOP3: ~20 of the ~60 staging instructions per block): an empty asm
+    // makes the value opaque, so it stays in a register for the duration of the ticket.
+    uint32_t trash = gc.trash_addr, acc_base = ctx.acc_addr, l32 = (uint32_t)lane;
+    asm volatile("" : "+r"(trash), "+r"(acc_base), "+r"(l32));
     // this lane loads entries l and l + 32 of a block: group l % EG, positions 2 (l / EG) and 2 (l / EG) + 1
     uint4 *my_slot = reinterpret_cast<uint4 *>(gc.stage + (((uint32_t)lane & (EG - 1u)) * K + 2u * ((uint32_t)lane / EG)));
     const uint2 *grp = gc.stage + g * K;
@@ -123,25 +127,22 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
     // the entries of the next two blocks are in flight while a block votes
     const uint32_t nblocks = (ngrab + 63u) / 64u;
     uint32_t c0, c1, n0, n1, m0, m1;
-    {
-        const uint32_t l = (uint32_t)lane;
-        c0 = l < ngrab ? __ldg(ent) : 0u;              c1 = l + 32u < ngrab ? __ldg(ent + 32) : 0u;
-        n0 = l + 64u < ngrab ? __ldg(ent + 64) : 0u;   n1 = l + 96u < ngrab ? __ldg(ent + 96) : 0u;
-    }
+    c0 = l32 < ngrab ? __ldg(ent) : 0u;              c1 = l32 + 32u < ngrab ? __ldg(ent + 32) : 0u;
+    n0 = l32 + 64u < ngrab ? __ldg(ent + 64) : 0u;   n1 = l32 + 96u < ngrab ? __ldg(ent + 96) : 0u;
+    const uint32_t *__restrict__ pre = ent + 128;      // what the loop prefetches next
+    uint32_t pre_j = l32 + 128u;                       // its index within the grab
 #pragma unroll 1
     for (uint32_t blk = 0; blk < nblocks; blk++) {
         const uint32_t blk0 = blk * 64u;               // first entry of this block within the grab
-        {
-            const uint32_t j = blk0 + 128u + (uint32_t)lane;
-            m0 = j < ngrab ? __ldg(ent + blk0 + 128) : 0u;
-            m1 = j + 32u < ngrab ? __ldg(ent + blk0 + 160) : 0u;
-        }
+        m0 = pre_j < ngrab ? __ldg(pre) : 0u;
+        m1 = pre_j + 32u < ngrab ? __ldg(pre + 32) : 0u;
+        pre += 64; pre_j += 64u;
         const uint32_t nvalid = min(64u, ngrab - blk0);
-        uint32_t a0 = ctx.acc_addr + (c0 & kLocMask) * 4u, a1 = ctx.acc_addr + (c1 & kLocMask) * 4u;
+        uint32_t a0 = acc_base + (c0 & kLocMask) * 4u, a1 = acc_base + (c1 & kLocMask) * 4u;
         bool slow = ((c0 | c1) & kSlowBit) != 0u;
         if (nvalid < 64u) {
-            if ((uint32_t)lane >= nvalid) { a0 = trash; c0 = 0u; }
-            if ((uint32_t)lane + 32u >= nvalid) { a1 = trash; c1 = 0u; }
+            if (l32 >= nvalid) { a0 = trash; c0 = 0u; }
+            if (l32 + 32u >= nvalid) { a1 = trash; c1 = 0u; }
             slow = ((c0 | c1) & kSlowBit) != 0u;
         }
         __syncwarp();
