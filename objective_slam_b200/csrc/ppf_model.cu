@@ -5,11 +5,11 @@
 //
 // Differences from the reference, none of which change results:
 //  * no N*N float4 feature matrix: one fused kernel goes point pair -> feature bins
-//    -> FNV key (+ the vote payload theta_u), 8 B written per pair instead of 20 B;
+//    -> FNV key, 8 B written per pair (key + pair index) instead of 20 B;
 //  * pair indices are u32 (N <= 46340, the reference's own int limit) so the radix
 //    sort moves 8 B per pair and pass instead of 12 B;
-//  * the vote payload (chunk-local m_r, alpha_m as a 19-bit binary angle) is
-//    gathered into bucket order once, so voting streams 4 B per vote.
+//  * the vote payload (chunk-local m_r, alpha_m as a 20-bit binary angle) is
+//    computed in bucket order once, so voting streams 4 B per vote.
 #include <cub/cub.cuh>
 #include <atomic>
 #include <cstdio>
@@ -322,34 +322,24 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
 // Model table build
 // ---------------------------------------------------------------------------------
 // One thread per ordered model pair p = m_r*N + m_i (coalesced along m_i):
-//   key[p]   = FNV-1a of the quantised feature (0 for the self pair)   -- ppf_kernel + ppf_hash_kernel
-//   theta[p] = 19-bit binary angle of u = (T_mg m_i).yz, bit 31 = slow  -- alpha_m of Drost et al.
+//   key[p] = FNV-1a of the quantised feature (0 for the self pair)   -- ppf_kernel + ppf_hash_kernel
+//   idx[p] = p                                                          -- the sort's payload (hashkeyToDataMap)
 __global__ void __launch_bounds__(256) model_pairs_kernel(const float4 *__restrict__ pos,
-                                                          const float4 *__restrict__ nrm,
-                                                          const float4 *__restrict__ fy,
-                                                          const float4 *__restrict__ fz, int n, float d_dist,
-                                                          float inv_d, uint32_t *keys, uint32_t *theta,
-                                                          int *max_kd) {
+                                                          const float4 *__restrict__ nrm, int n, float d_dist,
+                                                          float inv_d, uint32_t *keys, uint32_t *idx, int *max_kd) {
     size_t total = (size_t)n * n;
     int local_max = -1;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
         int r = (int)(p / n), i = (int)(p - (size_t)r * n);
-        uint32_t key = 0, th = 0;
+        uint32_t key = 0;
         if (r != i) {
             PointN a = load_point(pos, nrm, r), b = load_point(pos, nrm, i);
             FeatureBins fb = pair_feature_bins(a, b, d_dist, inv_d);
             key = feature_key(fb.kd, fb.k1, fb.k2, fb.k3, d_dist);
             if (fb.kd >= 0) local_max = max(local_max, fb.kd);
-            float4 y = __ldg(fy + r), z = __ldg(fz + r);
-            FrameYZ f;
-            f.y[0] = y.x; f.y[1] = y.y; f.y[2] = y.z; f.y[3] = y.w;
-            f.z[0] = z.x; f.z[1] = z.y; f.z[2] = z.z; f.z[3] = z.w;
-            float uy, uz;
-            frame_apply_yz(f, b.x, b.y, b.z, uy, uz);
-            th = theta_code(uy, uz);
         }
         keys[p] = key;
-        theta[p] = th;
+        idx[p] = (uint32_t)p;
     }
     local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 16));
     local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 8));
@@ -359,20 +349,28 @@ __global__ void __launch_bounds__(256) model_pairs_kernel(const float4 *__restri
     if ((threadIdx.x & 31) == 0 && local_max >= 0) atomicMax(max_kd, local_max);
 }
 
-__global__ void iota_kernel(uint32_t *v, size_t n) {
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        v[i] = (uint32_t)i;
-}
-
-// entries[q] = [theta : 20 | slow : 1 | m_r - chunk_base : 11] for sorted position q
-__global__ void gather_entries_kernel(const uint32_t *__restrict__ map, const uint32_t *__restrict__ theta,
-                                      size_t total, int n, int chunk_rows, uint32_t *entries) {
+// entries[q] = [theta : 20 | slow : 1 | m_r - chunk_base : 11] for sorted position q, where theta = 20-bit binary
+// angle of u = (T_mg m_i).yz (alpha_m of Drost et al.), bit 31 of theta_code = slow.  theta is COMPUTED here from
+// the pair the sort put at q (two L2-resident point loads + ~150 instructions) instead of being written per pair
+// before the sort and gathered after it: that gather was a random 4-byte read per pair (a 32-byte sector each,
+// 1.7 ms for 1e8 pairs) and needed an N^2 scratch array.
+__global__ void __launch_bounds__(256) entries_kernel(const uint32_t *__restrict__ map, const float4 *__restrict__ pos,
+                                                      const float4 *__restrict__ fy, const float4 *__restrict__ fz,
+                                                      size_t total, int n, int chunk_rows, uint32_t *entries) {
     for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
-        uint32_t p = map[q];
-        uint32_t th = __ldg(theta + p);
-        uint32_t r = p / (uint32_t)n;
-        uint32_t loc = r % (uint32_t)chunk_rows;
-        entries[q] = pack_entry(loc, th);
+        const uint32_t p = map[q];
+        const uint32_t r = p / (uint32_t)n, i = p - r * (uint32_t)n;
+        uint32_t th = 0;
+        if (r != i) {
+            const float4 y = __ldg(fy + r), z = __ldg(fz + r), b = __ldg(pos + i);
+            FrameYZ f;
+            f.y[0] = y.x; f.y[1] = y.y; f.y[2] = y.z; f.y[3] = y.w;
+            f.z[0] = z.x; f.z[1] = z.y; f.z[2] = z.z; f.z[3] = z.w;
+            float uy, uz;
+            frame_apply_yz(f, b.x, b.y, b.z, uy, uz);
+            th = theta_code(uy, uz);
+        }
+        entries[q] = pack_entry(r % (uint32_t)chunk_rows, th);
     }
 }
 
@@ -481,30 +479,27 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, total));
     const size_t cub_tmp = std::max(sort_tmp, std::max(rle_tmp, scan_tmp));
     Workspace ws;
-    int rc = ws.reserve(4 * total * 4 + cub_tmp + 64);
+    int rc = ws.reserve(3 * total * 4 + cub_tmp + 64);
     if (rc) return rc;
-    uint32_t *keys = ws.take<uint32_t>(total), *theta = ws.take<uint32_t>(total);
+    uint32_t *keys = ws.take<uint32_t>(total);
     uint32_t *keys_sorted = ws.take<uint32_t>(total), *iota = ws.take<uint32_t>(total);
     uint32_t *d_U = ws.take<uint32_t>(1);
     int *d_maxkd = ws.take<int>(1);
     void *tmp = ws.take_bytes(cub_tmp);
     struct Release { Workspace &w; ~Release() { w.release(); } } release_on_exit{ws};
-    if (!keys || !theta || !keys_sorted || !iota || !d_U || !d_maxkd || !tmp) {
+    if (!keys || !keys_sorted || !iota || !d_U || !d_maxkd || !tmp) {
         set_last_error("model: scratch arena too small");
         return PPF_ERR_CUDA;
     }
     PPF_CUDA_TRY(cudaMemsetAsync(d_maxkd, 0xFF, 4, 0));
     int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-    model_pairs_kernel<<<grid, 256>>>(m.cloud.pos, m.cloud.nrm, m.cloud.fy, m.cloud.fz, n, m.d_dist,
-                                      m.inv_d_dist, keys, theta, d_maxkd);
+    model_pairs_kernel<<<grid, 256>>>(m.cloud.pos, m.cloud.nrm, n, m.d_dist, m.inv_d_dist, keys, iota, d_maxkd);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
 
     // sort (key, pair index): LSD radix sort, stable, so every bucket ascends in pair index
     m.map = (uint32_t *)pool_alloc(total * 4, &m.map_cap);      // the two N^2 arrays come from the block cache
     if (!m.map) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
-    iota_kernel<<<grid, 256>>>(iota, total);
-    count_launch();
     PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, keys, keys_sorted, iota, m.map, total));
 
     // run-length encode -> unique keys + counts (histogram(), util.hpp:30-52); scan -> first index.
@@ -552,7 +547,7 @@ int model_build(ModelTable &m) {
     // vote payload in bucket order, per-chunk bucket slices, cell table
     m.entries = (uint32_t *)pool_alloc(total * 4, &m.entries_cap);
     if (!m.entries) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
-    gather_entries_kernel<<<grid, 256>>>(m.map, theta, total, n, m.chunk_rows, m.entries);
+    entries_kernel<<<grid, 256>>>(m.map, m.cloud.pos, m.cloud.fy, m.cloud.fz, total, n, m.chunk_rows, m.entries);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(pooled_malloc(&m.ranges, (size_t)m.U * m.n_chunks * sizeof(uint2)));
