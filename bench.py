@@ -147,7 +147,9 @@ def run_reference(args, rank):
     df = max(1, REFS_PER_GPU_DF // args.gpus)
     mp, mn, sp, sn, d, _ = make_workload()
     cores = os.cpu_count() or 1
-    refs, stride = cores, 10
+    # bounded sample per step, smaller when many steps are asked for (the whole run must end within minutes;
+    # the oracle rebuilds its model table inside every call, ~3 s, untimed)
+    refs, stride = cores, (10 if args.warmup + args.steps <= 8 else 25)
     times, pairs, votes, build = [], 0, 0, 0.0
     for i in range(args.warmup + args.steps):
         r = cpu.time_voting(mp, mn, sp, sn, d, df, max_refs=refs, threads=cores, scene_stride=stride)
@@ -176,7 +178,8 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=None,
+                    help="timed steps (default: 20 for the GPU arm -- p50 over >= 20 runs, SURVEY 8d -- and 5 for --impl reference)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -186,6 +189,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.steps is None:
+        args.steps = 5 if args.impl == "reference" else 20
     if args.impl == "reference":
         run_reference(args, rank)
         return
