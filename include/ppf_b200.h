@@ -173,6 +173,14 @@ int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const 
 int ppf_lookup_copy_survivors(const ppf_lookup_t *lk, uint64_t *codes_dst_dev, uint32_t *counts_dst_dev);
 int ppf_lookup_poses(const ppf_model_t *model, const ppf_scene_t *scene, ppf_lookup_t *lk);
 int ppf_lookup_cluster(const ppf_model_t *model, ppf_lookup_t *lk);
+/* Multi-GPU clustering of a merged survivor list (Model::ClusterTransformations is quadratic in dense cells):
+ * rank `shard` of `n_shards` scores the poses shard, shard + n_shards, ...; the caller sums the score arrays of
+ * all ranks (entries outside a slice are 0), writes the sum back and lets ppf_lookup_cluster_finish pick
+ * max_idx (model.cu:293-295).  Not available with use_averaged_clusters. */
+int ppf_lookup_cluster_shard(const ppf_model_t *model, ppf_lookup_t *lk, int shard, int n_shards);
+int ppf_lookup_copy_scores(const ppf_lookup_t *lk, float *scores_dst_dev);
+int ppf_lookup_set_scores(ppf_lookup_t *lk, const float *scores_src_dev);
+int ppf_lookup_cluster_finish(ppf_lookup_t *lk);
 /* cpu_clustering = true variant: PCL-style greedy clustering of the survivors on one host
  * core (transformation_clustering.cpp:62-137, model.cu:246-266); writes the best cluster's
  * averaged pose (row-major 4x4) = cpu_transformations[0] of ppf.cu:75-77. */

@@ -25,7 +25,8 @@ EXPORTS = [
     "ppf_lookup_create", "ppf_lookup_destroy", "ppf_model_lookup", "ppf_lookup_vote",
     "ppf_lookup_local_max", "ppf_lookup_finalize", "ppf_lookup_survivors", "ppf_lookup_set_survivors",
     "ppf_lookup_copy_survivors",
-    "ppf_lookup_poses", "ppf_lookup_cluster", "ppf_lookup_cluster_cpu", "ppf_lookup_get_stats",
+    "ppf_lookup_poses", "ppf_lookup_cluster", "ppf_lookup_cluster_shard", "ppf_lookup_copy_scores",
+    "ppf_lookup_set_scores", "ppf_lookup_cluster_finish", "ppf_lookup_cluster_cpu", "ppf_lookup_get_stats",
     "ppf_lookup_get", "ppf_vote_histogram", "ppf_registration",
 ]
 
@@ -104,6 +105,10 @@ def _load():
     L.ppf_lookup_copy_survivors.argtypes = [vp, vp, vp]
     L.ppf_lookup_poses.argtypes = [vp, vp, vp]
     L.ppf_lookup_cluster.argtypes = [vp, vp]
+    L.ppf_lookup_cluster_shard.argtypes = [vp, vp, ci, ci]
+    L.ppf_lookup_copy_scores.argtypes = [vp, vp]
+    L.ppf_lookup_set_scores.argtypes = [vp, vp]
+    L.ppf_lookup_cluster_finish.argtypes = [vp]
     L.ppf_lookup_cluster_cpu.argtypes = [vp, vp, vp]
     L.ppf_lookup_get_stats.argtypes = [vp, P(LookupStats)]
     L.ppf_lookup_get.argtypes = [vp] * 9

@@ -176,6 +176,7 @@ class Model:
         self.d_dist = float(d_dist)
         self.vote_count_threshold = float(vote_count_threshold)
         self.cpu_clustering = bool(cpu_clustering)
+        self.use_averaged_clusters = bool(use_averaged_clusters)
         self._lookup = None
 
     # -- persistent model database ------------------------------

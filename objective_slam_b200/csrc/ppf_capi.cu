@@ -257,6 +257,36 @@ int ppf_lookup_cluster(const ppf_model_t *m, ppf_lookup_t *lk) {
     return PPF_OK;
 }
 
+// Multi-GPU: the clustering of the merged survivor list is quadratic in dense cells (6 ms at K = 50k, 332 ms at
+// K = 396k), so every rank scores an interleaved slice, the slices are summed (all other entries are 0: exact)
+// and ppf_lookup_cluster_finish picks the winner.
+int ppf_lookup_cluster_shard(const ppf_model_t *m, ppf_lookup_t *lk, int shard, int n_shards) {
+    PPF_CHECK_ARG(m && lk && n_shards >= 1 && shard >= 0 && shard < n_shards, "cluster_shard: bad argument");
+    PPF_CHECK_ARG(!m->table.use_averaged_clusters || n_shards == 1,
+                  "cluster_shard: use_averaged_clusters needs every pose's averaged translation: cluster unsharded");
+    return cluster_run(m->table, lk->res, shard, n_shards);
+}
+int ppf_lookup_copy_scores(const ppf_lookup_t *lk, float *scores_dst_dev) {
+    PPF_CHECK_ARG(lk && (lk->res.K == 0 || scores_dst_dev), "copy_scores: NULL argument");
+    if (lk->res.K) PPF_CUDA_TRY(cudaMemcpy(scores_dst_dev, lk->res.scores, lk->res.K * 4, cudaMemcpyDeviceToDevice));
+    return PPF_OK;
+}
+int ppf_lookup_set_scores(ppf_lookup_t *lk, const float *scores_src_dev) {
+    PPF_CHECK_ARG(lk && (lk->res.K == 0 || scores_src_dev), "set_scores: NULL argument");
+    if (lk->res.K) PPF_CUDA_TRY(cudaMemcpy(lk->res.scores, scores_src_dev, lk->res.K * 4, cudaMemcpyDeviceToDevice));
+    return PPF_OK;
+}
+int ppf_lookup_cluster_finish(ppf_lookup_t *lk) {
+    PPF_CHECK_ARG(lk, "cluster_finish: NULL handle");
+    int rc = cluster_finish(lk->res);
+    cudaEventRecord(lk->ev[3], 0);
+    if (rc) return rc;
+    PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[3]));
+    cudaEventElapsedTime(&lk->stats.ms_pose_cluster, lk->ev[2], lk->ev[3]);
+    lk->stats.max_idx = lk->res.max_idx;
+    return PPF_OK;
+}
+
 int ppf_model_lookup(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk) {
     int rc = ppf_lookup_vote(m, s, df, 0, 1, lk);
     if (rc) return rc;

@@ -154,7 +154,8 @@ size_t order_survivors_bytes(size_t K);
 int  vote_reserve_K(VoteResult &r, size_t K);
 void vote_result_free(VoteResult &r);
 int  poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r);
-int  cluster_run(const ModelTable &m, VoteResult &r);
+int  cluster_run(const ModelTable &m, VoteResult &r, int shard = 0, int n_shards = 1);
+int  cluster_finish(VoteResult &r);
 int  voxel_grid_run(const float *xyz, int xs, const float *nrm, int ns, int n, int mem, float leaf, float *out_xyz,
                     float *out_nrm, int *n_out);
 int  op_point_pair_feature(const float *p1, const float *n1, const float *p2, const float *n2, size_t n, float d_dist,

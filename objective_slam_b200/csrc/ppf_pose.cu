@@ -134,13 +134,14 @@ __global__ void cellhash_kernel(const float3 *trans, uint32_t *cell_hash, uint32
 __global__ void cluster_kernel(const float3 *trans_in, const float4 *quats, const float *weights,
                                const uint32_t *adj_hash, const uint32_t *sorted_hash, const uint32_t *sorted_idx,
                                float *scores, float3 *trans_out, int count, float trans_thresh, int use_l1_norm,
-                               int use_averaged_clusters) {
+                               int use_averaged_clusters, int shard, int n_shards) {
     if (count <= 1) return;
     const float rot_thresh = 2 * d_angle0();                                  // ROT_THRESH, kernel.h:17
     const float rot_thresh_sq = rot_thresh * rot_thresh;
     const int lane = threadIdx.x & 31;
     const int warps = (gridDim.x * blockDim.x) >> 5;
-    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < count; idx += warps) {
+    // poses idx = shard, shard + n_shards, ... (multi-GPU: every rank scores an interleaved slice of the merged list)
+    for (int idx = shard + n_shards * ((blockIdx.x * blockDim.x + threadIdx.x) >> 5); idx < count; idx += n_shards * warps) {
         const float3 tt = trans_in[idx];
         const float4 q = quats[idx];
         float score = 1;
@@ -334,7 +335,23 @@ int poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r) {
     return PPF_OK;
 }
 
-int cluster_run(const ModelTable &m, VoteResult &r) {
+int cluster_finish(VoteResult &r) {
+    const int K = (int)r.K;
+    r.max_idx = 0;
+    if (K <= 1) return PPF_OK;
+    uint32_t *d_arg = nullptr;
+    PPF_CUDA_TRY(pooled_malloc(&d_arg, 4));
+    argmax_kernel<<<1, 1024>>>(r.scores, K, d_arg);
+    count_launch();
+    cudaError_t e = cudaMemcpy(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost);
+    pooled_free(d_arg);
+    PPF_CUDA_TRY(e);
+    return PPF_OK;
+}
+
+// shard / n_shards: score only the poses idx = shard (mod n_shards); the other scores stay 0 and max_idx is not
+// computed (cluster_finish does that once the slices of all ranks have been summed).  n_shards = 1: everything.
+int cluster_run(const ModelTable &m, VoteResult &r, int shard, int n_shards) {
     const int K = (int)r.K;
     r.max_idx = 0;
     if (K == 0) return PPF_OK;
@@ -366,9 +383,12 @@ int cluster_run(const ModelTable &m, VoteResult &r) {
     // rot_clustering_kernel updates translations in place while neighbours read them (a race in the
     // reference when use_averaged_clusters is set); we read a snapshot instead, which is deterministic.
     PPF_CUDA_TRY(cudaMemcpyAsync(tin, r.trans, (size_t)K * sizeof(float3), cudaMemcpyDeviceToDevice, 0));
-    cluster_kernel<<<(int)std::min<size_t>(((size_t)K * 32 + 255) / 256, 148 * 64), 256>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
-                                           m.d_dist, m.use_l1_norm, m.use_averaged_clusters);
+    const size_t mine = ((size_t)K + n_shards - 1) / n_shards;
+    cluster_kernel<<<(int)std::min<size_t>((mine * 32 + 255) / 256, 148 * 64), 256>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
+                                           m.d_dist, m.use_l1_norm, m.use_averaged_clusters, shard, n_shards);
     count_launch();
+    PPF_CUDA_TRY(cudaGetLastError());
+    if (n_shards > 1) return PPF_OK;
     argmax_kernel<<<1, 1024>>>(r.scores, K, d_arg);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());

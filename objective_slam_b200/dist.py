@@ -6,7 +6,9 @@ reference point against a replicated model table.  Only two tiny exchanges coupl
 required by the reference's semantics (model.cu:160-170):
   1. all_reduce(MAX) of the largest accumulator cell -> the global threshold count > thr * max;
   2. all_gather of each rank's surviving (code, count) list (exact parity needs every survivor,
-     not a truncated top-k), after which pose computation and clustering run replicated.
+     not a truncated top-k), after which pose computation runs replicated;
+  3. clustering of the merged list is sharded too (every rank scores an interleaved slice of the poses against
+     all of them) and the score slices are summed with one all_reduce, after which every rank picks the winner.
 One process per GPU, torch.distributed over NCCL (gloo on CPU for the tests).
 """
 from __future__ import annotations
@@ -87,5 +89,16 @@ def lookup_sharded(model, scene, lookup, rank: int, world: int, group=None, arra
         torch.cuda.synchronize()
         C.check(C.lib.ppf_lookup_set_survivors(lookup._h, codes.data_ptr(), counts.data_ptr(), codes.numel()))
     C.check(C.lib.ppf_lookup_poses(model._h, scene._h, lookup._h))
-    C.check(C.lib.ppf_lookup_cluster(model._h, lookup._h))
+    if world > 1 and not getattr(model, "use_averaged_clusters", True):
+        # 3. clustering of the merged list is quadratic in dense cells (332 ms at K = 396k on one GPU): every rank
+        # scores an interleaved slice, the slices are summed (entries outside a slice are 0, so the sum is exact)
+        C.check(C.lib.ppf_lookup_cluster_shard(model._h, lookup._h, rank, world))
+        scores = torch.zeros(max(codes.numel(), 1), dtype=torch.float32, device=dev)
+        C.check(C.lib.ppf_lookup_copy_scores(lookup._h, scores.data_ptr()))
+        dist.all_reduce(scores, op=dist.ReduceOp.SUM, group=group)
+        torch.cuda.synchronize()
+        C.check(C.lib.ppf_lookup_set_scores(lookup._h, scores.data_ptr()))
+        C.check(C.lib.ppf_lookup_cluster_finish(lookup._h))
+    else:
+        C.check(C.lib.ppf_lookup_cluster(model._h, lookup._h))
     return lookup.result(arrays=arrays)

@@ -210,3 +210,35 @@ def test_scene_size_hint_selects_the_layout_not_the_result():
     finally:
         if forced is not None:
             os.environ["PPF_B200_VOTE"] = forced
+
+
+def test_sharded_clustering_equals_unsharded():
+    """Multi-GPU path: clustering scores computed in 3 interleaved slices and summed are the unsharded scores,
+    bit for bit, and the winner is the same (one GPU plays the three ranks in turn)."""
+    import ctypes
+    import torch
+    import objective_slam_b200 as ppf
+    from objective_slam_b200 import _capi as C
+    mp, mn, sp, sn, d, _ = _case(1200, 5000, seed=17)
+    m, s = ppf.Model(mp, mn, d), ppf.Scene(sp, sn, d, 2)
+    whole = m.ppf_lookup(s)
+    K = whole.num_top_votes
+    assert K > 100
+    lk = m._lookup if getattr(m, "_lookup", None) is not None else ppf.Lookup()
+    C.check(C.lib.ppf_lookup_vote(m._h, s._h, 2, 0, 1, lk._h))
+    C.check(C.lib.ppf_lookup_finalize(m._h, whole.max_vote_count, lk._h))
+    C.check(C.lib.ppf_lookup_poses(m._h, s._h, lk._h))
+    total = torch.zeros(K, dtype=torch.float32, device="cuda")
+    part = torch.zeros(K, dtype=torch.float32, device="cuda")
+    for r in range(3):
+        C.check(C.lib.ppf_lookup_cluster_shard(m._h, lk._h, r, 3))
+        C.check(C.lib.ppf_lookup_copy_scores(lk._h, part.data_ptr()))
+        assert int((part != 0).sum()) == len(range(r, K, 3))
+        total += part
+    torch.cuda.synchronize()
+    C.check(C.lib.ppf_lookup_set_scores(lk._h, total.data_ptr()))
+    C.check(C.lib.ppf_lookup_cluster_finish(lk._h))
+    got = lk.result()
+    assert got.max_idx == whole.max_idx
+    assert (got.vote_counts_out.view(np.uint32) == whole.vote_counts_out.view(np.uint32)).all()
+    assert (got.pose.view(np.uint32) == whole.pose.view(np.uint32)).all()

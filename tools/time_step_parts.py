@@ -8,7 +8,7 @@ import bench
 mp, mn, sp, sn, d, T = bench.make_workload()
 dev = torch.device("cuda", 0)
 sp_d, sn_d = torch.from_numpy(sp).to(dev), torch.from_numpy(sn).to(dev)
-model = ppf.Model(mp, mn, d); lk = ppf.Lookup(); df = 8
+model = ppf.Model(mp, mn, d); lk = ppf.Lookup(); df = int(os.environ.get("DF", "8"))
 def tick(label, fn, acc):
     torch.cuda.synchronize(); t = time.perf_counter(); r = fn(); torch.cuda.synchronize()
     acc.setdefault(label, []).append((time.perf_counter() - t) * 1e3); return r
