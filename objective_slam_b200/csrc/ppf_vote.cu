@@ -14,7 +14,7 @@
 //     hits (bucket slice, alpha_s) into a shared-memory queue with one warp-aggregated
 //     atomic per warp;
 //   * phase 2 lets each warp drain hits: 32 lanes read 32 consecutive 4-byte bucket
-//     entries (one 128 B line), derive the alpha bin from two 19-bit binary angles and
+//     entries (one 128 B line), derive the alpha bin from two 20-bit binary angles and
 //     add to the shared accumulator with ATOMS.  A vote whose angle falls within a
 //     guard band of a bin edge recomputes alpha exactly as trans_model_scene does
 //     (kernel.cu:302-342), which keeps every count bit-exact;
