@@ -31,7 +31,7 @@ namespace ppf {
 
 constexpr uint32_t kGTile       = kHitQueue;        // scene points per phase-1 tile (the scene's tile AABBs)
 constexpr int      kGStage      = 64;               // entries staged per warp per block (two per lane)
-constexpr uint32_t kGGrabVotes  = 8192;             // votes per scheduler ticket of a grouped piece
+constexpr uint32_t kGGrabVotes  = 32768;            // votes per scheduler ticket of a grouped piece (8192: 699 ms, 16384: 685, 32768: 679, 65536: 689 on configs[1])
 constexpr int      kGItemsMax   = 16;               // queue records per thread in the ticket scan
 // hit record: [bucket : 20 | (theta_v + half) : 20 | slow : 1 | stored scene index : 23]
 constexpr int      kGBucketShift = 44;
