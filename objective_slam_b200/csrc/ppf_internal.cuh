@@ -33,7 +33,9 @@ constexpr int kVoteBatch    = 256;           // bucket entries per inner pass: 8
 constexpr int kVoteGrab     = 2048;          // bucket entries one warp takes per scheduler grab
 // grouped vote kernel (ppf_vote_grouped.cu): a bigger hit queue (all hits of a reference point, sorted by
 // bucket) in exchange for a smaller accumulator chunk
-constexpr int kGroupedMaxRows = 480;         // 31 * (480 + 1) * 4 B = 59,644 B + 8,192 B entry stage + 13,312 hits x 12 B
+constexpr int kGroupedMaxRows = 640;         // 31 * (640 + 1) * 4 B = 79,484 B + 16,384 B entry stage + 11,264 hits x 12 B
+                                             // (configs[1], 10k-point model: 384 rows 692 ms, 480 683, 576 675, 640 670,
+                                             //  704 712 -- there the queue no longer holds the hits of the heaviest points)
 // accumulator row stride: chunk_rows is a multiple of 32, so +1 makes bank = (bin + row) mod 32 --
 // lanes that hit the same model point with different alpha bins (the common case inside a bucket,
 // whose entries are sorted by m_r) fall into different banks.

@@ -17,7 +17,7 @@
 //     entry is fetched once per HG hits and decoded once (staged in shared memory as
 //     (entry, row address)), and a vote costs 5 instructions (IADD, IMAD.WIDE, VIADDMNMX, IMAD, ATOMS)
 //     + half an LDS.128;
-//   * the accumulator chunk is small (<= 480 model points x 31 bins) so that the queue holds ~12,000 hits; a
+//   * the accumulator chunk is small (<= 640 model points x 31 bins) so that the queue holds ~11,000 hits; a
 //     reference point with more hits than that (dense scenes) is handed to a second instantiation of the
 //     kernel that cuts the scene into segments and parks the chunk accumulators in global scratch between them.
 // tools/microbench/grouped_vote.cu: 14.2 / 11-13 / 9-11 votes/clk/SM at HG = 32 / 16 / 8 against 6.1 for
