@@ -342,7 +342,7 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
         a.cell2bucket = m.cell2bucket; a.ranges = m.ranges; a.entries = m.entries; a.map = m.map;
         a.n_chunks = m.n_chunks; a.chunk_rows = m.chunk_rows;
-        a.queue_cap = 0; a.n_splits = 1; a.sched = nullptr; a.acc_scratch = nullptr;
+        a.queue_cap = 0; a.sched = nullptr; a.acc_scratch = nullptr;
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;
         a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
         a.scalars = r.scalars; a.totals = r.votes_total;

@@ -26,7 +26,7 @@ struct VoteArgs {
     int n_chunks, chunk_rows;
     // grouped kernel only: hit queue capacity (records); work counters: sched[0] = next reference point,
     // sched[1 + r] = next chunk of reference point r (zeroed before the launch)
-    int queue_cap, n_splits;
+    int queue_cap;
     uint32_t *sched;
     uint32_t *acc_scratch;                        // [CTAs][n_chunks][31 x S]: accumulators parked between scene segments
     // output

@@ -274,8 +274,8 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     __syncthreads();
 
     // ---- phase 1 for one tile of scene points: pairs (s_r, s_i) -> hit queue (tile / warp culling as in
-    // vote_kernel).  flt != nullptr would keep only hits whose bucket has entries in that chunk (unused now).
-    auto collect_tile = [&](uint32_t base, const uint2 *__restrict__ flt) {
+    // vote_kernel).  Every hit whose cell exists in the table is queued, whatever the chunk.
+    auto collect_tile = [&](uint32_t base) {
         const PointN R = s_R;
         const FrameYZ FS = s_FS;
         if (box_dist2(R, __ldg(a.tbox_lo + base / kGTile), __ldg(a.tbox_hi + base / kGTile)) >= a.cull_r2) return;
@@ -293,7 +293,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                 FeatureBins fb = pair_feature_bins(R, O, a.d_dist, a.inv_d);
                 if (fb.kd >= 0 && fb.kd < a.K_d) {
                     const uint32_t b = __ldg(a.cell2bucket + cell_index(fb.kd, fb.k1, fb.k2, fb.k3));
-                    if (b != kNoBucket && (flt == nullptr || __ldg(flt + b).y != 0u)) {
+                    if (b != kNoBucket) {
                         float vy, vz;
                         frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
                         const uint32_t tc = theta_code(vy, vz);
@@ -498,7 +498,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
         int seg = -1;
         if constexpr (!SEGMENTS) {
             // ---- first pass: all hits of the reference point, whatever the chunk
-            for (uint32_t base0 = 0; base0 < (uint32_t)a.ns; base0 += kGTile) collect_tile(base0, nullptr);
+            for (uint32_t base0 = 0; base0 < (uint32_t)a.ns; base0 += kGTile) collect_tile(base0);
             __syncthreads();
             n = s_nhits;
             if (n > Q) {
@@ -525,7 +525,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                     if (tid == 0) s_nhits = 0;
                     __syncthreads();
                     while (base < (uint32_t)a.ns && s_nhits + kGTile <= Q) {
-                        collect_tile(base, nullptr);
+                        collect_tile(base);
                         base += kGTile;
                         __syncthreads();
                     }
@@ -635,7 +635,6 @@ int vote_grouped_launch(VoteArgs a, int ref_count) {
     }
     // persistent CTAs (one per SM: the kernel takes all of its shared memory) draw (reference point, chunk)
     // work from the counters in a.sched (zeroed by the caller)
-    a.n_splits = 1;
     const long long grid = vote_grouped_ctas();
     const size_t smem = vote_grouped_smem(a.chunk_rows);
     PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
