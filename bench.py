@@ -138,6 +138,22 @@ def cpu_baseline_drost_m(mp, mn, sp, sn, d, df):
                       f"model_description {r['build_seconds']:.1f} s, not counted)"}
 
 
+def cpu_baseline_pcl_style(mp, mn, sp, sn, d, df):
+    """Drost's registration organised like PCL's PPFEstimation / PPFRegistration (alpha_m precomputed per model
+    pair, one alpha_s per scene pair, per-reference accumulator, greedy pose clustering), restated in C
+    (oracle/pcl_style.c; PCL is not installed: parity unpinned) and timed on the host cores on a bounded sample of
+    the same workload.  The strongest CPU comparator: a vote is a subtraction and a table increment."""
+    from oracle import cpu
+    cores = os.cpu_count() or 1
+    refs, stride = 2 * cores, 2
+    r = cpu.pcl_style(mp, mn, sp, sn, d, ref_rate=df, max_refs=refs, scene_stride=stride, threads=cores)
+    return {"value": r["pairs"] / r["seconds"], "unit": "pairs/s", "cores": cores, "kind": "port",
+            "votes_per_s": r["votes"] / r["seconds"], "model_build_s": round(r["build_seconds"], 3),
+            "sample": f"{refs} reference points spread over the scene x every {stride}nd of the {len(sp)} scene points "
+                      f"({r['pairs']} pairs, {r['votes']} votes, {r['seconds']:.1f} s voting + clustering on {cores} threads; "
+                      f"model table {r['build_seconds']:.1f} s, not counted)"}
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU path (oracle port; the MATLAB/Octave and PCL originals cannot run
     here: no Octave, MATLAB, Java or PCL in the image), all host threads, bounded sample per step."""
@@ -345,6 +361,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(mp, mn, sp, sn, d, df)
             line["cpu_baseline_drost_m"] = cpu_baseline_drost_m(mp, mn, sp, sn, d, df)
+            line["cpu_baseline_pcl_style"] = cpu_baseline_pcl_style(mp, mn, sp, sn, d, df)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

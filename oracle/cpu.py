@@ -141,6 +141,26 @@ def drost_m(mpts, mnrm, spts, snrm, d_dist=0.0, skip=5, max_refs=0, threads=0, s
     return dict(seconds=s, build_seconds=build_s.value, pairs=pairs.value, votes=votes.value, pose=pose)
 
 
+def pcl_style(mpts, mnrm, spts, snrm, d_dist, ref_rate=5, max_refs=0, threads=0, scene_stride=1):
+    """oracle/pcl_style.c: Drost's registration organised like PCL's PPFRegistration (alpha_m precomputed, one
+    alpha_s per scene pair, per-reference accumulator, greedy pose clustering).  Timing baseline, parity unpinned.
+    Returns dict(seconds, build_seconds, pairs, votes, pose[4,4] float64)."""
+    L = lib()
+    vp, ci, cd, cf = ctypes.c_void_p, ctypes.c_int, ctypes.c_double, ctypes.c_float
+    L.pcl_style_run.restype = cd
+    L.pcl_style_run.argtypes = [vp, vp, ci, vp, vp, ci, cf, ci, ci, ci, ci, ctypes.POINTER(ctypes.c_uint64),
+                                ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(cd), vp]
+    mpts, mnrm, spts, snrm = _f32(mpts), _f32(mnrm), _f32(spts), _f32(snrm)
+    pairs, votes, build_s = ctypes.c_uint64(), ctypes.c_uint64(), cd()
+    pose = np.zeros((4, 4), np.float64)
+    s = L.pcl_style_run(_p(mpts), _p(mnrm), len(mpts), _p(spts), _p(snrm), len(spts), float(d_dist), int(ref_rate),
+                        int(max_refs), int(scene_stride), int(threads), ctypes.byref(pairs), ctypes.byref(votes),
+                        ctypes.byref(build_s), pose.ctypes.data)
+    if s < 0:
+        raise ValueError("pcl_style: models of >= 65536 points are not supported")
+    return dict(seconds=s, build_seconds=build_s.value, pairs=pairs.value, votes=votes.value, pose=pose)
+
+
 def time_voting(mpts, mnrm, spts, snrm, d_dist, ref_df=1, max_refs=0, threads=0, scene_stride=1):
     """Seconds spent voting over (up to max_refs) reference points; returns dict."""
     mpts, mnrm, spts, snrm = _f32(mpts), _f32(mnrm), _f32(spts), _f32(snrm)
