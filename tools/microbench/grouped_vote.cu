@@ -17,7 +17,10 @@ __device__ __forceinline__ void red_shared(uint32_t addr) {
 }
 
 // HG = 0: classical (lane = entry, one hit per warp pass)
-template <int HG>
+// VAR (grouped loops only): 0 = staged (entry, row address) pairs, LDS.128 per two votes [what the kernel does];
+// 1 = staged raw 4-byte entries, LDS.128 per four votes + LOP3 / IADD decode per vote;
+// 2 = entries held in registers (lane j holds entry j of the block) and broadcast by SHFL, no staging (HG = 32).
+template <int HG, int VAR = 0>
 __global__ void __launch_bounds__(1024) bench(unsigned long long *cycles, unsigned *sink, int per_row) {
     extern __shared__ __align__(16) unsigned char smem[];
     uint32_t *acc = reinterpret_cast<uint32_t *>(smem);
@@ -57,21 +60,53 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *cycles, unsign
             __syncwarp();
             stage[lane] = make_uint2(e, acc_base + row * 4);
             __syncwarp();
-            const uint4 *src = reinterpret_cast<const uint4 *>(stage + g * K);
+            if constexpr (VAR == 0) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(stage + g * K);
 #pragma unroll
-            for (int k = 0; k < K / 2; k++) {
-                uint4 q = src[k];
-                {
-                    uint32_t d = hit - q.x;
-                    unsigned long long p = (unsigned long long)d * 30ull;
-                    worst = max(worst, (uint32_t)p - 0x56000u);
-                    red_shared((uint32_t)(p >> 32) * (S * 4) + q.y);
+                for (int k = 0; k < K / 2; k++) {
+                    uint4 q = src[k];
+                    {
+                        uint32_t d = hit - q.x;
+                        unsigned long long p = (unsigned long long)d * 30ull;
+                        worst = max(worst, (uint32_t)p - 0x56000u);
+                        red_shared((uint32_t)(p >> 32) * (S * 4) + q.y);
+                    }
+                    {
+                        uint32_t d = hit - q.z;
+                        unsigned long long p = (unsigned long long)d * 30ull;
+                        worst = max(worst, (uint32_t)p - 0x56000u);
+                        red_shared((uint32_t)(p >> 32) * (S * 4) + q.w);
+                    }
                 }
-                {
-                    uint32_t d = hit - q.z;
+            } else if constexpr (VAR == 1) {
+                // raw entries [theta : 20 | 0 | row * 4 : 11]: restage them in the low half of the slots
+                uint32_t *raw = reinterpret_cast<uint32_t *>(stage);
+                __syncwarp();
+                raw[lane] = e | (row * 4 & 0x7FCu);
+                __syncwarp();
+                const uint4 *src = reinterpret_cast<const uint4 *>(raw + g * K);
+#pragma unroll
+                for (int k = 0; k < K / 4; k++) {
+                    const uint4 q = src[k];
+                    const uint32_t ee[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        uint32_t d = hit - ee[u];
+                        unsigned long long p = (unsigned long long)d * 30ull;
+                        worst = max(worst, (uint32_t)p - 0x56000u);
+                        red_shared((uint32_t)(p >> 32) * (S * 4) + ((ee[u] & 0x7FCu) + acc_base));
+                    }
+                }
+            } else {
+                // registers + SHFL: lane j keeps (entry, address) of entry j; step k broadcasts lane k's pair
+                const uint32_t my_e = e, my_a = acc_base + row * 4;
+#pragma unroll
+                for (int k = 0; k < 32; k++) {
+                    const uint32_t qe = __shfl_sync(0xffffffffu, my_e, k), qa = __shfl_sync(0xffffffffu, my_a, k);
+                    uint32_t d = hit - qe;
                     unsigned long long p = (unsigned long long)d * 30ull;
                     worst = max(worst, (uint32_t)p - 0x56000u);
-                    red_shared((uint32_t)(p >> 32) * (S * 4) + q.w);
+                    red_shared((uint32_t)(p >> 32) * (S * 4) + qa);
                 }
             }
         }
@@ -84,15 +119,15 @@ __global__ void __launch_bounds__(1024) bench(unsigned long long *cycles, unsign
     if (x == 0xdeadbeef) sink[0] = x;
 }
 
-template <int HG>
+template <int HG, int VAR = 0>
 void run(const char *name, int per_row) {
     int nsm = 148, threads = 1024;
     unsigned *sink; unsigned long long *cyc;
     cudaMalloc(&sink, 4); cudaMalloc(&cyc, nsm * 8);
     size_t smem = (BINS * S * 4 + 15) / 16 * 16 + 32 * STAGE * 8;
-    cudaFuncSetAttribute(bench<HG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    bench<HG><<<nsm, threads, smem>>>(cyc, sink, per_row);
-    bench<HG><<<nsm, threads, smem>>>(cyc, sink, per_row);
+    cudaFuncSetAttribute(bench<HG, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    bench<HG, VAR><<<nsm, threads, smem>>>(cyc, sink, per_row);
+    bench<HG, VAR><<<nsm, threads, smem>>>(cyc, sink, per_row);
     cudaDeviceSynchronize();
     unsigned long long h[148]; cudaMemcpy(h, cyc, nsm * 8, cudaMemcpyDeviceToHost);
     double avg = 0; for (int i = 0; i < nsm; i++) avg += h[i]; avg /= nsm;
@@ -108,6 +143,9 @@ int main() {
         run<8>("grouped HG=8", per_row);
         run<16>("grouped HG=16", per_row);
         run<32>("grouped HG=32", per_row);
+        run<32, 1>("grouped HG=32, raw entries", per_row);
+        run<8, 1>("grouped HG=8, raw entries", per_row);
+        run<32, 2>("grouped HG=32, regs + SHFL", per_row);
     }
     return 0;
 }
