@@ -62,7 +62,7 @@ const char *ppf_last_error(void);
 const char *ppf_version(void);
 /* Number of kernels of this library launched by the process so far (diagnostic; bench.py's gpu_launches). */
 uint64_t ppf_kernel_launch_count(void);
-/* Destroyed scenes / models park their device block in a small cache (<= 16 blocks, <= 6 GB) so that a
+/* Destroyed scenes / models park their device block in a small cache (<= 64 blocks, <= 6 GB) so that a
  * recognition loop does not call cudaMalloc / cudaFree per frame; this returns the cached blocks to the driver. */
 void ppf_release_cached_memory(void);
 /* Optional hint for ppf_model_create: how many points the scenes have that the next models will be matched against
@@ -101,6 +101,11 @@ int ppf_model_load(const char *path, ppf_model_t **out);
 /* How the table is laid out for voting: accumulator chunks, model points per chunk, and which vote kernel serves
  * it (1 = grouped, ppf_vote_grouped.cu; 0 = one hit per warp pass, ppf_vote.cu).  Any output may be NULL. */
 int ppf_model_layout(const ppf_model_t *model, int *n_chunks, int *chunk_rows, int *grouped_kernel);
+
+/* The options a model handle carries (the reference's Model members, model.h:43-46), e.g. after ppf_model_load.
+ * Any output may be NULL. */
+int ppf_model_params(const ppf_model_t *model, float *d_dist, float *vote_count_threshold, int *use_l1_norm,
+                     int *use_averaged_clusters);
 
 /* ParallelHashArray contents: U unique sorted keys, counts, first index, and the
  * N*N-long key-ordered map of pair indices (m_r*N + m_i).  size_t-typed like the
@@ -198,6 +203,13 @@ int ppf_lookup_get(const ppf_lookup_t *lk, uint64_t *votes, uint32_t *counts, fl
 int ppf_vote_histogram(const ppf_model_t *model, const ppf_scene_t *scene,
                        unsigned ref_point_downsample_factor, uint64_t *codes_out,
                        uint32_t *counts_out, size_t capacity, size_t *n_out);
+
+/* The same for one shard of the reference points only (shard_rank / shard_count as in ppf_lookup_vote: reference
+ * point number shard_rank + k * shard_count of the points with s_r % ref_point_downsample_factor == 0): full-size
+ * parity checks against a sample of reference points (oracle Mode B). */
+int ppf_vote_histogram_shard(const ppf_model_t *model, const ppf_scene_t *scene,
+                             unsigned ref_point_downsample_factor, int shard_rank, int shard_count,
+                             uint64_t *codes_out, uint32_t *counts_out, size_t capacity, size_t *n_out);
 
 /* ---- The drop-in boundary -------------------------------------------------------- */
 typedef struct ppf_cloud {

@@ -20,14 +20,14 @@ EXPORTS = [
     "ppf_last_error", "ppf_version", "ppf_kernel_launch_count", "ppf_release_cached_memory", "ppf_set_expected_scene_points",
     "ppf_scene_create", "ppf_scene_destroy", "ppf_scene_num_points", "ppf_scene_features",
     "ppf_model_create", "ppf_model_destroy", "ppf_model_num_points", "ppf_model_save", "ppf_model_load",
-    "ppf_model_layout", "ppf_model_table_sizes",
+    "ppf_model_layout", "ppf_model_params", "ppf_model_table_sizes",
     "ppf_model_table_get", "ppf_model_features", "ppf_point_pair_feature", "ppf_trans_model_scene", "ppf_voxel_grid",
     "ppf_lookup_create", "ppf_lookup_destroy", "ppf_model_lookup", "ppf_lookup_vote",
     "ppf_lookup_local_max", "ppf_lookup_finalize", "ppf_lookup_survivors", "ppf_lookup_set_survivors",
     "ppf_lookup_copy_survivors",
     "ppf_lookup_poses", "ppf_lookup_cluster", "ppf_lookup_cluster_shard", "ppf_lookup_copy_scores",
     "ppf_lookup_set_scores", "ppf_lookup_cluster_finish", "ppf_lookup_cluster_cpu", "ppf_lookup_get_stats",
-    "ppf_lookup_get", "ppf_vote_histogram", "ppf_registration",
+    "ppf_lookup_get", "ppf_vote_histogram", "ppf_vote_histogram_shard", "ppf_registration",
 ]
 
 
@@ -87,6 +87,7 @@ def _load():
     L.ppf_model_save.argtypes = [vp, ctypes.c_char_p]
     L.ppf_model_load.argtypes = [ctypes.c_char_p, P(vp)]
     L.ppf_model_layout.argtypes = [vp, P(ci), P(ci), P(ci)]
+    L.ppf_model_params.argtypes = [vp, P(cf), P(cf), P(ci), P(ci)]
     L.ppf_model_table_sizes.argtypes = [vp, P(sz), P(sz)]
     L.ppf_model_table_get.argtypes = [vp, vp, vp, vp, vp]
     L.ppf_model_features.argtypes = [vp, ci, ci, ci, ci, vp, vp]
@@ -113,6 +114,7 @@ def _load():
     L.ppf_lookup_get_stats.argtypes = [vp, P(LookupStats)]
     L.ppf_lookup_get.argtypes = [vp] * 9
     L.ppf_vote_histogram.argtypes = [vp, vp, cu, vp, vp, sz, P(sz)]
+    L.ppf_vote_histogram_shard.argtypes = [vp, vp, cu, ci, ci, vp, vp, sz, P(sz)]
     L.ppf_registration.argtypes = [P(CloudDesc), ci, P(CloudDesc), ci, vp, cu, cf, ci, ci, ci, ci, vp, vp, vp]
     return L
 

@@ -166,6 +166,7 @@ class Model:
         it only selects the table layout / vote kernel (ppf_set_expected_scene_points), never the results."""
         xp, xs, np_, ns, n, mem, keep = _as_cloud_arrays(points, normals)
         self._h = ctypes.c_void_p()
+        self._lookup = None
         C.lib.ppf_set_expected_scene_points(int(expected_scene_points))
         try:
             C.check(C.lib.ppf_model_create(xp, xs, np_, ns, n, mem, float(d_dist), float(vote_count_threshold),
@@ -176,8 +177,8 @@ class Model:
         self.d_dist = float(d_dist)
         self.vote_count_threshold = float(vote_count_threshold)
         self.cpu_clustering = bool(cpu_clustering)
+        self.use_l1_norm = bool(use_l1_norm)
         self.use_averaged_clusters = bool(use_averaged_clusters)
-        self._lookup = None
 
     # -- persistent model database ------------------------------
     def save(self, path: str):
@@ -189,12 +190,16 @@ class Model:
         """Model handle from a file written by save(): no rebuild (ppf_model_load)."""
         self = cls.__new__(cls)
         self._h = ctypes.c_void_p()
+        self._lookup = None                         # before the load can fail: __del__ -> close() reads it
         C.check(C.lib.ppf_model_load(os.fsencode(path), ctypes.byref(self._h)))
         self.n = int(C.lib.ppf_model_num_points(self._h))
-        self.d_dist = None
-        self.vote_count_threshold = None
+        d, thr, l1, avg = ctypes.c_float(), ctypes.c_float(), ctypes.c_int(), ctypes.c_int()
+        C.check(C.lib.ppf_model_params(self._h, ctypes.byref(d), ctypes.byref(thr), ctypes.byref(l1), ctypes.byref(avg)))
+        self.d_dist = float(d.value)
+        self.vote_count_threshold = float(thr.value)
+        self.use_l1_norm = bool(l1.value)
+        self.use_averaged_clusters = bool(avg.value)
         self.cpu_clustering = bool(cpu_clustering)
-        self._lookup = None
         return self
 
     def layout(self):
@@ -225,16 +230,18 @@ class Model:
         return ppf, keys
 
     # -- voting_scheme -------------------------------------------------------------
-    def vote_histogram(self, scene: Scene):
-        """All unique vote codes and their counts (ascending code), before thresholding."""
+    def vote_histogram(self, scene: Scene, shard_rank: int = 0, shard_count: int = 1):
+        """All unique vote codes and their counts (ascending code), before thresholding; optionally for one shard
+        of the reference points only (reference point number shard_rank + k * shard_count)."""
         n = ctypes.c_size_t()
-        C.check(C.lib.ppf_vote_histogram(self._h, scene._h, scene.ref_point_downsample_factor, None, None, 0,
-                                         ctypes.byref(n)))
+        df = scene.ref_point_downsample_factor
+        C.check(C.lib.ppf_vote_histogram_shard(self._h, scene._h, df, shard_rank, shard_count, None, None, 0,
+                                               ctypes.byref(n)))
         codes = np.empty(n.value, np.uint64)
         counts = np.empty(n.value, np.uint32)
         if n.value:
-            C.check(C.lib.ppf_vote_histogram(self._h, scene._h, scene.ref_point_downsample_factor, codes.ctypes.data,
-                                             counts.ctypes.data, n.value, ctypes.byref(n)))
+            C.check(C.lib.ppf_vote_histogram_shard(self._h, scene._h, df, shard_rank, shard_count, codes.ctypes.data,
+                                                   counts.ctypes.data, n.value, ctypes.byref(n)))
         return codes, counts
 
     def ppf_lookup(self, scene: Scene, arrays: bool = True) -> LookupResult:
@@ -252,7 +259,7 @@ class Model:
         return res
 
     def close(self):
-        if self._lookup is not None:
+        if getattr(self, "_lookup", None) is not None:
             self._lookup.close()
             self._lookup = None
         if getattr(self, "_h", None) and C is not None and getattr(C, "lib", None) is not None:

@@ -126,6 +126,16 @@ int ppf_model_layout(const ppf_model_t *m, int *n_chunks, int *chunk_rows, int *
     return PPF_OK;
 }
 
+int ppf_model_params(const ppf_model_t *m, float *d_dist, float *vote_count_threshold, int *use_l1_norm,
+                     int *use_averaged_clusters) {
+    PPF_CHECK_ARG(m, "model is NULL");
+    if (d_dist) *d_dist = m->table.d_dist;
+    if (vote_count_threshold) *vote_count_threshold = m->table.vote_count_threshold;
+    if (use_l1_norm) *use_l1_norm = m->table.use_l1_norm;
+    if (use_averaged_clusters) *use_averaged_clusters = m->table.use_averaged_clusters;
+    return PPF_OK;
+}
+
 int ppf_model_table_sizes(const ppf_model_t *m, size_t *U, size_t *npairs) {
     PPF_CHECK_ARG(m, "model is NULL");
     if (U) *U = m->table.U;
@@ -287,14 +297,19 @@ int ppf_lookup_cluster_finish(ppf_lookup_t *lk) {
     return PPF_OK;
 }
 
-int ppf_model_lookup(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk) {
+// gpu_clustering = false: stop after the poses (the caller clusters on the host, Model::ppf_lookup with
+// cpu_clustering set never runs ClusterTransformations, model.cu:284-291)
+static int lookup_run(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk, bool gpu_clustering) {
     int rc = ppf_lookup_vote(m, s, df, 0, 1, lk);
     if (rc) return rc;
     if ((rc = ppf_lookup_finalize(m, lk->stats.max_vote_count, lk))) return rc;
     if ((rc = ppf_lookup_poses(m, s, lk))) return rc;
-    if ((rc = ppf_lookup_cluster(m, lk))) return rc;
+    if (gpu_clustering && (rc = ppf_lookup_cluster(m, lk))) return rc;
     if (lk->stats.num_nonunique_votes == 0) { set_last_error("lookup: no scene pair matched the model"); return PPF_ERR_NO_VOTES; }
     return PPF_OK;
+}
+int ppf_model_lookup(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk) {
+    return lookup_run(m, s, df, lk, true);
 }
 
 int ppf_lookup_get_stats(const ppf_lookup_t *lk, ppf_lookup_stats_t *stats) {
@@ -329,9 +344,14 @@ int ppf_lookup_get(const ppf_lookup_t *lk, uint64_t *votes, uint32_t *counts, fl
 
 int ppf_vote_histogram(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, uint64_t *codes_out,
                        uint32_t *counts_out, size_t capacity, size_t *n_out) {
+    return ppf_vote_histogram_shard(m, s, df, 0, 1, codes_out, counts_out, capacity, n_out);
+}
+
+int ppf_vote_histogram_shard(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, int shard_rank, int shard_count,
+                             uint64_t *codes_out, uint32_t *counts_out, size_t capacity, size_t *n_out) {
     PPF_CHECK_ARG(m && s && n_out, "histogram: NULL argument");
     VoteResult r;
-    int rc = vote_run(m->table, s->cloud, df, 0, 1, 1, r, nullptr, nullptr);
+    int rc = vote_run(m->table, s->cloud, df, shard_rank, shard_count, 1, r, nullptr, nullptr);
     uint32_t h[4] = {0, 0, 0, 0};
     if (!rc && r.scalars) {
         if (cudaMemcpy(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) rc = PPF_ERR_CUDA;
@@ -462,7 +482,10 @@ extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes,
     int ndev = 0;
     PPF_CUDA_TRY(cudaGetDeviceCount(&ndev));
     if (ndev < 1) { set_last_error("registration: no CUDA device"); return PPF_ERR_CUDA; }
+    int caller_device = 0;
+    PPF_CUDA_TRY(cudaGetDevice(&caller_device));
     PPF_CUDA_TRY(cudaSetDevice(std::min(ndev - 1, std::max(device, 0))));   // ppf.cu:45
+    struct RestoreDevice { int d; ~RestoreDevice() { cudaSetDevice(d); } } restore_device{caller_device};
     std::memset(poses_out, 0, (size_t)num_scenes * num_models * 64);
     // The reference rebuilds Scene and Model for every (scene, model) pair (ppf.cu:63-70). The model
     // table depends only on (model, d_dist), so it is built once per model and reused across scenes;
@@ -488,7 +511,7 @@ extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes,
         rc = ppf_scene_create(c.xyz, c.xyz_stride, c.nrm, c.nrm_stride, c.n, PPF_MEM_HOST, &scene);
         for (int j = 0; j < num_models && !rc; j++) {
             float *pose = poses_out + ((size_t)i * num_models + j) * 16;
-            int st = ppf_model_lookup(models[j], scene, ref_point_downsample_factor, lk);
+            int st = lookup_run(models[j], scene, ref_point_downsample_factor, lk, !cpu_clustering);
             if (st == PPF_OK) {
                 if (cpu_clustering) st = ppf_lookup_cluster_cpu(models[j], lk, pose);      // ppf.cu:75-77
                 else st = ppf_lookup_get(lk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pose);

@@ -20,7 +20,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <atomic>
+#include <mutex>
 #include <string>
+#include <vector>
 
 #include "ppf_math.cuh"
 
@@ -53,7 +55,23 @@ struct Cloud {
     size_t block_cap = 0;                              // (nullptr for a cloud read by model_load)
     float4 *gbox_lo = nullptr, *gbox_hi = nullptr;     // AABB of every 32-point group
     float4 *tbox_lo = nullptr, *tbox_hi = nullptr;     // AABB of every kHitQueue-point tile
+    float bb_lo[3] = {0.f, 0.f, 0.f}, bb_hi[3] = {0.f, 0.f, 0.f};   // AABB of the finite points (scene clouds; host copy)
 };
+
+// Scene-side feature cells BEYOND the model's distance range (kd >= K_d) whose 32-bit FNV key equals a model key.
+// The reference matches scene pairs to model buckets by key equality alone (ppf_vote_count_kernel,
+// kernel.cu:480-501), so such a far pair votes for the colliding bucket.  cell2bucket covers kd < K_d; this
+// list (a handful of cells: #cells x U / 2^32) covers the rest, hashed lazily up to the extent of the largest
+// scene the model has met.  cell id = kd * 17^3 + (k1 * 17 + k2) * 17 + k3.
+struct FarCells {
+    std::mutex mu;
+    int K_scanned = 0;                                  // cells with kd in [K_d, K_scanned) have been hashed
+    std::vector<unsigned long long> cells_h;            // ascending
+    std::vector<uint32_t> buckets_h;
+    unsigned long long *cells = nullptr;                // device copies (pooled)
+    uint32_t *buckets = nullptr;
+};
+constexpr int kMaxDistBins = 1 << 22;                   // quant_bin is exact below 2^22 bins
 
 struct ModelTable {
     Cloud cloud;
@@ -68,6 +86,7 @@ struct ModelTable {
     int K_d = 0;
     uint32_t *cell2bucket = nullptr;
     float *weights = nullptr;                 // modelPointVoteWeights, all 1.0 (model.cu:67)
+    FarCells *far = nullptr;                  // lazily filled cache (owned; see model_far_cells)
     // options carried by the reference's Model object (model.h:43-46)
     float vote_count_threshold = 0.4f;
     int use_l1_norm = 0, use_averaged_clusters = 0;
@@ -147,6 +166,8 @@ int  model_build(ModelTable &m);
 void model_free(ModelTable &m);
 int  model_save(const ModelTable &m, const char *path);
 int  model_load(ModelTable &m, const char *path);
+int  model_far_cells(const ModelTable &m, const Cloud &scene, const unsigned long long **cells, const uint32_t **buckets,
+                     int *n, int *kd_min, int *kd_max);
 int  model_table_get(const ModelTable &m, uint32_t *hashkeys, size_t *counts, size_t *first, size_t *map);
 int  vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_rank, int shard_count,
               int emit_all, VoteResult &r, unsigned long long *pairs_out, int *launches);

@@ -11,7 +11,9 @@
 //  * the vote payload (chunk-local m_r, alpha_m as a 20-bit binary angle) is
 //    computed in bucket order once, so voting streams 4 B per vote.
 #include <cub/cub.cuh>
+#include <algorithm>
 #include <atomic>
+#include <cmath>
 #include <cstdio>
 #include <mutex>
 #include <unordered_map>
@@ -55,6 +57,10 @@ constexpr size_t kPoolMaxBlocks = 64;
 constexpr size_t kPoolMaxBytes = (size_t)6 << 30;
 }  // namespace
 
+// device every block handed out by pool_alloc was allocated on (a handle may be destroyed while another device is
+// current -- ppf_registration switches devices, Python finalizers run at any time)
+static std::unordered_map<void *, int> g_block_device;
+
 void *pool_alloc(size_t bytes, size_t *cap_out) {
     int dev = 0;
     cudaGetDevice(&dev);
@@ -77,27 +83,33 @@ void *pool_alloc(size_t bytes, size_t *cap_out) {
         pool_trim();                                  // give the cached blocks back and try once more
         if (cudaMalloc(&p, bytes) != cudaSuccess) return nullptr;
     }
+    {
+        std::lock_guard<std::mutex> lock(g_pool_mutex);
+        g_block_device[p] = dev;
+    }
     *cap_out = bytes;
     return p;
 }
 void pool_free(void *p, size_t cap) {
     if (!p) return;
-    int dev = 0;
-    cudaGetDevice(&dev);
     {
         std::lock_guard<std::mutex> lock(g_pool_mutex);
+        int dev = 0;
+        auto it = g_block_device.find(p);
+        if (it != g_block_device.end()) dev = it->second; else cudaGetDevice(&dev);
         size_t total = cap;
         for (auto &b : g_pool) total += b.cap;
         if (g_pool.size() < kPoolMaxBlocks && total <= kPoolMaxBytes) {
             g_pool.push_back({p, cap, dev});
             return;
         }
+        g_block_device.erase(p);
     }
     cudaFree(p);
 }
 void pool_trim() {
     std::lock_guard<std::mutex> lock(g_pool_mutex);
-    for (auto &b : g_pool) cudaFree(b.ptr);
+    for (auto &b : g_pool) { cudaFree(b.ptr); g_block_device.erase(b.ptr); }
     g_pool.clear();
 }
 
@@ -222,8 +234,10 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
         dx = tx; dn = tn;
     }
     const int grid = std::min((n + 255) / 256, 148 * 8);
+    float *mm_dev = nullptr;
     if (spatial_sort) {
         float *mm = ws.take<float>(6);
+        mm_dev = mm;
         uint32_t *key = ws.take<uint32_t>(n), *key_s = ws.take<uint32_t>(n), *idx = ws.take<uint32_t>(n);
         void *tmp = ws.take_bytes(sort_tmp);
         c.order = ws.take<uint32_t>(n); c.inv = ws.take<uint32_t>(n);
@@ -249,6 +263,12 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
         boxes_kernel<<<std::min((nt + 127) / 128, 148 * 8), 128>>>(c.pos, n, kHitQueue, c.tbox_lo, c.tbox_hi, nt);
         count_launch();
         PPF_CUDA_TRY(cudaGetLastError());
+    }
+    if (spatial_sort && mm_dev) {                       // host copy of the AABB: bounds the distance bins of the scene's pairs
+        float mm_h[6];
+        PPF_CUDA_TRY(cudaMemcpyAsync(mm_h, mm_dev, sizeof(mm_h), cudaMemcpyDeviceToHost, 0));
+        PPF_CUDA_TRY(cudaStreamSynchronize(0));
+        for (int k = 0; k < 3; k++) { c.bb_lo[k] = mm_h[k]; c.bb_hi[k] = mm_h[3 + k]; }
     }
     PPF_CUDA_TRY(cudaStreamSynchronize(0));
     return PPF_OK;
@@ -422,6 +442,96 @@ __global__ void cell_table_kernel(const uint32_t *__restrict__ hashkeys, uint32_
     }
 }
 
+// Far cells: hash every cell with kd in [kd0, kd1) the way ppf_hash_kernel would and keep those whose key is a model
+// key (kernel.cu:480-501 matches by key equality alone).  Expected output: #cells x U / 2^32 entries.
+__global__ void far_cells_kernel(const uint32_t *__restrict__ hashkeys, uint32_t U, int kd0, int kd1, float d_dist,
+                                 unsigned long long *cells, uint32_t *buckets, uint32_t cap, uint32_t *count) {
+    const unsigned long long total = (unsigned long long)(kd1 - kd0) * kCellsPerDist;
+    for (unsigned long long t = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; t < total;
+         t += (unsigned long long)gridDim.x * blockDim.x) {
+        const int kd = kd0 + (int)(t / kCellsPerDist);
+        int r = (int)(t % kCellsPerDist);
+        const int k3 = r % kAngleCells; r /= kAngleCells;
+        const int k2 = r % kAngleCells, k1 = r / kAngleCells;
+        const uint32_t key = feature_key(kd, k1, k2, k3, d_dist);
+        if (key == 0u) continue;
+        uint32_t lo = 0, hi = U;
+        while (lo < hi) {
+            const uint32_t mid = lo + ((hi - lo) >> 1);
+            if (__ldg(hashkeys + mid) < key) lo = mid + 1; else hi = mid;
+        }
+        if (lo < U && __ldg(hashkeys + lo) == key) {
+            const uint32_t slot = atomicAdd(count, 1u);
+            if (slot < cap) { cells[slot] = (unsigned long long)kd * kCellsPerDist + (unsigned long long)(t % kCellsPerDist); buckets[slot] = lo; }
+        }
+    }
+}
+
+// The far cells a scene of this extent can reach (kd below the scene's longest possible pair), as device arrays
+// sorted by cell id.  Hashes the missing distance bins on first use and caches them in the model handle.
+int model_far_cells(const ModelTable &m, const Cloud &scene, const unsigned long long **cells, const uint32_t **buckets,
+                    int *n, int *kd_min, int *kd_max) {
+    *cells = nullptr; *buckets = nullptr; *n = 0; *kd_min = 0; *kd_max = -1;
+    if (!m.far || m.K_d <= 0 || m.U == 0 || scene.n <= 1) return PPF_OK;
+    // longest pair of the scene <= diagonal of its AABB (non-finite points form no finite pair)
+    double diag2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+        const double e = (double)scene.bb_hi[k] - (double)scene.bb_lo[k];
+        if (e > 0.0) diag2 += e * e;
+    }
+    const double bins = std::sqrt(diag2) * 1.0001 / (double)m.d_dist + 2.0;
+    const int K_scene = (int)std::min<double>(bins, (double)kMaxDistBins);
+    if (K_scene <= m.K_d) return PPF_OK;
+    FarCells &fc = *m.far;
+    std::lock_guard<std::mutex> lock(fc.mu);
+    const int K_have = std::max(fc.K_scanned, m.K_d);
+    if (K_scene > K_have) {
+        const int K_new = (int)std::min<long long>(kMaxDistBins, ((long long)K_scene + 63) / 64 * 64);
+        uint32_t cap = 4096;
+        for (int attempt = 0; attempt < 2; attempt++) {
+            unsigned long long *dc = nullptr; uint32_t *db = nullptr, *dn = nullptr;
+            PPF_CUDA_TRY(pooled_malloc(&dc, (size_t)cap * 8)); PPF_CUDA_TRY(pooled_malloc(&db, (size_t)cap * 4));
+            PPF_CUDA_TRY(pooled_malloc(&dn, 4));
+            PPF_CUDA_TRY(cudaMemsetAsync(dn, 0, 4, 0));
+            const unsigned long long total = (unsigned long long)(K_new - K_have) * kCellsPerDist;
+            far_cells_kernel<<<(int)std::min<unsigned long long>((total + 255) / 256, 148 * 32), 256>>>(
+                m.hashkeys, m.U, K_have, K_new, m.d_dist, dc, db, cap, dn);
+            count_launch();
+            uint32_t cnt = 0;
+            cudaError_t e = cudaMemcpy(&cnt, dn, 4, cudaMemcpyDeviceToHost);
+            std::vector<unsigned long long> hc(std::min(cnt, cap));
+            std::vector<uint32_t> hb(hc.size());
+            if (e == cudaSuccess && !hc.empty()) e = cudaMemcpy(hc.data(), dc, hc.size() * 8, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && !hc.empty()) e = cudaMemcpy(hb.data(), db, hb.size() * 4, cudaMemcpyDeviceToHost);
+            pooled_free(dc); pooled_free(db); pooled_free(dn);
+            PPF_CUDA_TRY(e);
+            if (cnt > cap) { cap = cnt; continue; }                // rare: count, then fetch
+            std::vector<size_t> order(hc.size());
+            for (size_t i = 0; i < order.size(); i++) order[i] = i;
+            std::sort(order.begin(), order.end(), [&](size_t a, size_t b) { return hc[a] < hc[b]; });
+            for (size_t i : order) { fc.cells_h.push_back(hc[i]); fc.buckets_h.push_back(hb[i]); }   // new cells lie above the old
+            break;
+        }
+        fc.K_scanned = K_new;
+        pooled_free(fc.cells); pooled_free(fc.buckets);
+        fc.cells = nullptr; fc.buckets = nullptr;
+        if (!fc.cells_h.empty()) {
+            PPF_CUDA_TRY(pooled_malloc(&fc.cells, fc.cells_h.size() * 8));
+            PPF_CUDA_TRY(pooled_malloc(&fc.buckets, fc.buckets_h.size() * 4));
+            PPF_CUDA_TRY(cudaMemcpy(fc.cells, fc.cells_h.data(), fc.cells_h.size() * 8, cudaMemcpyHostToDevice));
+            PPF_CUDA_TRY(cudaMemcpy(fc.buckets, fc.buckets_h.data(), fc.buckets_h.size() * 4, cudaMemcpyHostToDevice));
+        }
+    }
+    // only the cells this scene can reach (the cache may cover a larger scene met earlier)
+    const unsigned long long lim = (unsigned long long)K_scene * kCellsPerDist;
+    const size_t cnt = std::lower_bound(fc.cells_h.begin(), fc.cells_h.end(), lim) - fc.cells_h.begin();
+    if (cnt == 0) return PPF_OK;
+    *cells = fc.cells; *buckets = fc.buckets; *n = (int)cnt;
+    *kd_min = (int)(fc.cells_h[0] / kCellsPerDist);
+    *kd_max = (int)(fc.cells_h[cnt - 1] / kCellsPerDist);
+    return PPF_OK;
+}
+
 __global__ void fill_kernel(float *v, int n, float x) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) v[i] = x;
@@ -433,6 +543,7 @@ void model_free(ModelTable &m) {
     if (m.map_cap) pool_free(m.map, m.map_cap); else pooled_free(m.map);
     if (m.entries_cap) pool_free(m.entries, m.entries_cap); else pooled_free(m.entries);
     pooled_free(m.ranges); pooled_free(m.cell2bucket); pooled_free(m.weights);
+    if (m.far) { pooled_free(m.far->cells); pooled_free(m.far->buckets); delete m.far; }
     m = ModelTable();
 }
 
@@ -448,6 +559,7 @@ int model_build(ModelTable &m) {
     if (!(m.d_dist > 0.f)) { set_last_error("model: d_dist must be > 0"); return PPF_ERR_INVALID; }
     m.inv_d_dist = 1.0f / m.d_dist;
     m.n_chunks = 1; m.chunk_rows = 32;
+    if (!m.far) m.far = new FarCells();
     PPF_CUDA_TRY(pooled_malloc(&m.weights, std::max(1, n) * sizeof(float)));
     if (n > 0) fill_kernel<<<(n + 255) / 256, 256>>>(m.weights, n, 1.0f);
     count_launch();
@@ -638,6 +750,66 @@ int model_save(const ModelTable &mc, const char *path) {
     return rc;
 }
 
+// A loaded table is used unchecked as indices by the vote kernels (shared-memory atomics, global gathers): reject a
+// corrupt or re-written file here instead of faulting on the GPU later.  flag bits name the array that failed.
+__global__ void validate_table_kernel(const uint32_t *__restrict__ counts, const uint32_t *__restrict__ first,
+                                      const uint32_t *__restrict__ hashkeys, const uint32_t *__restrict__ map,
+                                      const uint32_t *__restrict__ entries, const uint2 *__restrict__ ranges,
+                                      const uint32_t *__restrict__ cell2bucket, uint32_t U, size_t total, int n,
+                                      int n_chunks, int chunk_rows, size_t ncell, uint32_t *flag) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    uint32_t bad = 0;
+    for (size_t i = t0; i < U; i += stride) {
+        const uint32_t f = first[i], c = counts[i];
+        if (c == 0 || (size_t)f + c > total) bad |= 1u;
+        if (i + 1 < U ? (first[i + 1] != f + c || hashkeys[i + 1] <= hashkeys[i]) : ((size_t)f + c != total)) bad |= 1u;
+        if (i == 0 && f != 0) bad |= 1u;
+    }
+    for (size_t q = t0; q < total; q += stride) {
+        const uint32_t p = map[q];
+        if ((size_t)p >= total) { bad |= 2u; continue; }
+        // the entry's chunk-local row must be the row of the pair the map names
+        if ((entries[q] & kLocMask) != (p / (uint32_t)n) % (uint32_t)chunk_rows) bad |= 4u;
+    }
+    for (size_t t = t0; t < (size_t)U * n_chunks; t += stride) {
+        const uint2 r = ranges[t];
+        const uint32_t b = (uint32_t)(t % U);
+        if (r.x < first[b] || (size_t)r.x + r.y > (size_t)first[b] + counts[b]) bad |= 8u;
+        if (r.y && (size_t)r.x + r.y <= total) {    // the slice really holds rows of chunk c only
+            const int c = (int)(t / U);
+            const uint32_t r0 = map[r.x] / (uint32_t)n, r1 = map[r.x + r.y - 1] / (uint32_t)n;
+            if ((int)(r0 / (uint32_t)chunk_rows) != c || (int)(r1 / (uint32_t)chunk_rows) != c) bad |= 8u;
+        } else if (r.y) {
+            bad |= 8u;
+        }
+    }
+    for (size_t i = t0; i < ncell; i += stride) {
+        const uint32_t b = cell2bucket[i];
+        if (b != kNoBucket && b >= U) bad |= 16u;
+    }
+    if (bad) atomicOr(flag, bad);
+}
+
+static int model_validate(const ModelTable &m) {
+    if (m.cloud.n <= 1) return PPF_OK;
+    const size_t total = (size_t)m.cloud.n * m.cloud.n, ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
+    uint32_t *flag = nullptr, h = 0;
+    PPF_CUDA_TRY(pooled_malloc(&flag, 4));
+    cudaMemsetAsync(flag, 0, 4, 0);
+    validate_table_kernel<<<148 * 8, 256>>>(m.counts, m.first, m.hashkeys, m.map, m.entries, m.ranges, m.cell2bucket, m.U,
+                                            total, m.cloud.n, m.n_chunks, m.chunk_rows, ncell, flag);
+    count_launch();
+    cudaError_t e = cudaMemcpy(&h, flag, 4, cudaMemcpyDeviceToHost);
+    pooled_free(flag);
+    PPF_CUDA_TRY(e);
+    if (h) {
+        set_last_error("model load: corrupt table payload (failed checks, bit mask " + std::to_string(h) +
+                       ": 1 = keys/counts/first, 2 = map, 4 = entries, 8 = ranges, 16 = cell table)");
+        return PPF_ERR_INVALID;
+    }
+    return PPF_OK;
+}
+
 int model_load(ModelTable &m, const char *path) {
     FILE *f = fopen(path, "rb");
     if (!f) { set_last_error(std::string("model load: cannot open ") + path); return PPF_ERR_INVALID; }
@@ -653,6 +825,7 @@ int model_load(ModelTable &m, const char *path) {
     m.cloud.n = (int)h.n; m.U = h.U; m.K_d = (int)h.K_d; m.n_chunks = h.n_chunks; m.chunk_rows = h.chunk_rows;
     m.prefer_grouped = h.prefer_grouped; m.use_l1_norm = h.use_l1_norm; m.use_averaged_clusters = h.use_averaged_clusters;
     m.d_dist = h.d_dist; m.inv_d_dist = 1.0f / h.d_dist; m.vote_count_threshold = h.vote_count_threshold;
+    if (!m.far) m.far = new FarCells();
     std::vector<char> buf(kIoChunk);
     int rc = PPF_OK;
     for (auto &a : model_arrays(m)) {
@@ -661,6 +834,7 @@ int model_load(ModelTable &m, const char *path) {
     }
     if (!rc && fgetc(f) != EOF) { set_last_error("model load: trailing bytes"); rc = PPF_ERR_INVALID; }
     fclose(f);
+    if (!rc) rc = model_validate(m);
     return rc;
 }
 

@@ -88,16 +88,14 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
                 PointN O;
                 O.x = p.x; O.y = p.y; O.z = p.z; O.nx = q.x; O.ny = q.y; O.nz = q.z; O.nn = q.w;
                 FeatureBins fb = pair_feature_bins(R, O, a.d_dist, a.inv_d);
-                if (fb.kd >= 0 && fb.kd < a.K_d) {
-                    uint32_t b = __ldg(a.cell2bucket + cell_index(fb.kd, fb.k1, fb.k2, fb.k3));
-                    if (b != kNoBucket) {
-                        uint2 rg = __ldg(ranges + b);
-                        if (rg.y != 0) {
-                            float vy, vz;
-                            frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
-                            h = make_uint4(rg.x, rg.y, pack_hit_theta(theta_code(vy, vz)), (uint32_t)i);
-                            hit = true;
-                        }
+                const uint32_t b = probe_bucket(a, fb);
+                if (b != kNoBucket) {
+                    uint2 rg = __ldg(ranges + b);
+                    if (rg.y != 0) {
+                        float vy, vz;
+                        frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
+                        h = make_uint4(rg.x, rg.y, pack_hit_theta(theta_code(vy, vz)), (uint32_t)i);
+                        hit = true;
                     }
                 }
             }
@@ -332,9 +330,15 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         VoteArgs a;
         a.spos = scene.pos; a.snrm = scene.nrm; a.sfy = scene.fy; a.sfz = scene.fz; a.ns = ns;
         a.sinv = scene.inv; a.gbox_lo = scene.gbox_lo; a.gbox_hi = scene.gbox_hi; a.tbox_lo = scene.tbox_lo; a.tbox_hi = scene.tbox_hi;
-        {   // a pair at true distance >= (K_d + 1) d_dist (1 + 1e-4) has distance bin >= K_d even after the approximate
-            // sqrt (relative error ~1e-6): it cannot be in the table.  Conservative: everything nearer is processed.
-            const float r = (float)(m.K_d + 1) * m.d_dist * 1.0001f;
+        {   // far cells: scene features beyond the model's distance range whose FNV key equals a model key still vote
+            // in the reference (kernel.cu:480-501); usually there are none and the cull radius stays at the table's edge
+            int rc_far = model_far_cells(m, scene, &a.far_cells, &a.far_buckets, &a.n_far, &a.far_kd_min, &a.far_kd_max);
+            if (rc_far) return rc_far;
+            // a pair at true distance >= (K + 1) d_dist (1 + 1e-4) has distance bin >= K even after the approximate
+            // sqrt (relative error ~1e-6): with K = one past the last bin that can hit, it cannot vote.
+            // Conservative: everything nearer is processed.
+            const int K_hit = a.n_far ? std::max(m.K_d, a.far_kd_max + 1) : m.K_d;
+            const float r = (float)(K_hit + 1) * m.d_dist * 1.0001f;
             a.cull_r2 = r * r;
         }
         a.ref_start = shard_rank * (int)df; a.ref_stride = shard_count * (int)df; a.ref_count = R;

@@ -21,6 +21,10 @@ struct VoteArgs {
     int K_d;
     uint32_t U;
     const uint32_t *cell2bucket;
+    // cells beyond the model's distance range whose FNV key collides with a model key (FarCells; usually none)
+    const unsigned long long *far_cells;
+    const uint32_t *far_buckets;
+    int n_far, far_kd_min, far_kd_max;
     const uint2 *ranges;
     const uint32_t *entries, *map;
     int n_chunks, chunk_rows;
@@ -45,6 +49,24 @@ __device__ __forceinline__ FrameYZ load_frame(const float4 *__restrict__ fy, con
     f.y[0] = y.x; f.y[1] = y.y; f.y[2] = y.z; f.y[3] = y.w;
     f.z[0] = z.x; f.z[1] = z.y; f.z[2] = z.z; f.z[3] = z.w;
     return f;
+}
+
+// Probe: bucket of a quantised scene feature, or kNoBucket.  Replaces hash + lower_bound + key equality
+// (ParallelHashArray::GetIndices, ppf_vote_count_kernel kernel.cu:489-497): cells inside the model's distance
+// range through the cell table, cells beyond it (reachable only through a 32-bit key collision) through the short
+// sorted far-cell list.
+__device__ __forceinline__ uint32_t probe_bucket(const VoteArgs &a, const FeatureBins &fb) {
+    if (fb.kd < 0) return kNoBucket;                               // NaN / Inf distance: key 0 never matches
+    if (fb.kd < a.K_d) return __ldg(a.cell2bucket + cell_index(fb.kd, fb.k1, fb.k2, fb.k3));
+    if (fb.kd < a.far_kd_min || fb.kd > a.far_kd_max) return kNoBucket;
+    const unsigned long long id = (unsigned long long)fb.kd * kCellsPerDist +
+                                  (unsigned long long)((fb.k1 * kAngleCells + fb.k2) * kAngleCells + fb.k3);
+    int lo = 0, hi = a.n_far;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(a.far_cells + mid) < id) lo = mid + 1; else hi = mid;
+    }
+    return (lo < a.n_far && __ldg(a.far_cells + lo) == id) ? __ldg(a.far_buckets + lo) : kNoBucket;
 }
 
 // Voting context shared by the fast and the exact path.

@@ -292,17 +292,15 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                 PointN O;
                 O.x = p.x; O.y = p.y; O.z = p.z; O.nx = q.x; O.ny = q.y; O.nz = q.z; O.nn = q.w;
                 FeatureBins fb = pair_feature_bins(R, O, a.d_dist, a.inv_d);
-                if (fb.kd >= 0 && fb.kd < a.K_d) {
-                    const uint32_t b = __ldg(a.cell2bucket + cell_index(fb.kd, fb.k1, fb.k2, fb.k3));
-                    if (b != kNoBucket) {
-                        float vy, vz;
-                        frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
-                        const uint32_t tc = theta_code(vy, vz);
-                        const uint32_t th = ((tc & kThetaMask) + kThetaHalf) & kThetaMask;
-                        h = ((unsigned long long)b << kGBucketShift) | ((unsigned long long)th << kGThetaShift) |
-                            ((unsigned long long)(tc >> 31) << 23) | (unsigned long long)(uint32_t)i;
-                        hit = true;
-                    }
+                const uint32_t b = probe_bucket(a, fb);
+                if (b != kNoBucket) {
+                    float vy, vz;
+                    frame_apply_yz(FS, O.x, O.y, O.z, vy, vz);
+                    const uint32_t tc = theta_code(vy, vz);
+                    const uint32_t th = ((tc & kThetaMask) + kThetaHalf) & kThetaMask;
+                    h = ((unsigned long long)b << kGBucketShift) | ((unsigned long long)th << kGThetaShift) |
+                        ((unsigned long long)(tc >> 31) << 23) | (unsigned long long)(uint32_t)i;
+                    hit = true;
                 }
             }
             const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -525,7 +523,12 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                     __syncthreads();
                     if (tid == 0) s_nhits = 0;
                     __syncthreads();
-                    while (base < (uint32_t)a.ns && s_nhits + kGTile <= Q) {
+                    // block-uniform loop condition: every thread reads s_nhits between two barriers, before any
+                    // warp of the next collect_tile can bump it
+                    while (base < (uint32_t)a.ns) {
+                        const uint32_t have = s_nhits;
+                        __syncthreads();
+                        if (have + kGTile > Q) break;
                         collect_tile(base);
                         base += kGTile;
                         __syncthreads();

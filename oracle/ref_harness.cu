@@ -376,6 +376,119 @@ long ref_vote_histogram(void *hm, void *hs, unsigned long *codes_out, unsigned i
     return n;
 }
 
+// ---- Mode B: tiled oracle for sizes the whole-kernel replay cannot hold ------------------------
+// The reference materialises N_s^2 features, keys and one 8-byte code per vote (~60 N_s^2 bytes + 8 B per vote):
+// a 50k-point scene does not fit, a 1M-point scene overflows its int indices.  Scene reference points are
+// independent (the high 32 bits of a vote code are s_r, model.h:61-63), so Mode B replays the SAME per-pair and
+// per-vote steps for a LIST of reference points, streaming the scene, into a dense (m_r, alpha) histogram per
+// reference point.  All arithmetic is the reference's own device code, linked through -rdc: compute_ppf
+// (kernel.cu:109-122), disc_feature (:94-100), hash (:23-30), trans_model_scene (:302-349); the model table is
+// the reference's ParallelHashArray built by ref_model_create (Mode A).  Ours: the loops, lower_bound (the
+// std:: semantics thrust::lower_bound implements) and the hit test of ppf_vote_count_kernel (:489-497).
+// tests/test_modeb_gpu.py first shows Mode B == Mode A cell for cell on sizes both run.
+}  // extern "C"
+
+extern __device__ void trans_model_scene(float3 m_r, float3 n_r_m, float3 m_i, float3 s_r, float3 n_r_s, float3 s_i,
+                                         float d_dist, unsigned int &alpha_idx);
+
+__global__ void modeb_vote_kernel(const float3 *spts, const float3 *snrm, int ns, const int *refs, int R,
+                                  const float3 *mpts, const float3 *mnrm, int nm,
+                                  const unsigned int *hashKeys, const std::size_t *ppfCount,
+                                  const std::size_t *firstPPFIndex, const std::size_t *key2ppfMap, std::size_t U,
+                                  float d_dist, unsigned int *hist, unsigned long long *num_votes) {
+    const int lane = threadIdx.x & 31;
+    const long long warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    const long long total = (long long)R * ns;
+    unsigned long long mine = 0;
+    for (long long t = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; t < total; t += warps) {
+        const int r = (int)(t / ns), j = (int)(t - (long long)r * ns);
+        const int s_r = refs[r];
+        if (j == s_r) continue;                                          // ppf_kernel: .x = NaN -> key 0 (kernel.cu:437-441)
+        // ppf_kernel (kernel.cu:444-450) + ppf_hash_kernel (kernel.cu:466-471)
+        float4 f = disc_feature(compute_ppf(spts[s_r], snrm[s_r], spts[j], snrm[j]), d_dist, D_ANGLE0);
+        const unsigned int key = isnan(f.x) ? 0u : hash(&f, sizeof(float4));
+        // GetIndices = lower_bound (parallel_hash_array.hpp:81-92); hit test of ppf_vote_count_kernel (kernel.cu:489-497)
+        std::size_t lo = 0, hi = U;
+        while (lo < hi) {
+            const std::size_t mid = lo + (hi - lo) / 2;
+            if (hashKeys[mid] < key) lo = mid + 1; else hi = mid;
+        }
+        if (key == 0 || lo >= U || key != hashKeys[lo]) continue;
+        const std::size_t cnt = ppfCount[lo], first = firstPPFIndex[lo];
+        // ppf_vote_kernel's loop over the bucket (kernel.cu:536-550), 32 entries at a time
+        for (std::size_t i = lane; i < cnt; i += 32) {
+            const unsigned int modelPPFIndex = (unsigned int)key2ppfMap[first + i];
+            const unsigned int model_r_index = modelPPFIndex / nm;
+            const unsigned int model_i_index = modelPPFIndex - model_r_index * nm;
+            unsigned int alpha_idx;
+            trans_model_scene(mpts[model_r_index], mnrm[model_r_index], mpts[model_i_index],
+                              spts[s_r], snrm[s_r], spts[j], d_dist, alpha_idx);
+            atomicAdd(&hist[((std::size_t)r * nm + model_r_index) * 64 + (alpha_idx & 63u)], 1u);
+            mine++;
+        }
+    }
+    for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+    if (lane == 0 && mine) atomicAdd(num_votes, mine);
+}
+
+extern "C" {
+
+// Votes of the scene reference points refs[0..R) (caller's indices into the scene cloud, each must be a point the
+// lookup would use, i.e. s_r % ref_point_downsample_factor == 0) against model hm.  codes_out / counts_out receive
+// every non-zero accumulator cell as the reference's unique-vote code [s_r : 32 | m_r : 26 | alpha : 6] and its
+// count, ascending code order (what thrust::sort + histogram leave, model.cu:148-151).  Returns the number of
+// cells (nothing is written when it exceeds capacity), -1 on a CUDA error; *num_votes_out = votes cast.
+long ref_modeb_histogram(void *hm, const float *sxyz, const float *snrm, int ns, const int *refs, int R,
+                         unsigned long *codes_out, unsigned int *counts_out, long capacity,
+                         unsigned long *num_votes_out) {
+    RefModel *m = (RefModel *)hm;
+    if (num_votes_out) *num_votes_out = 0;
+    if (R <= 0 || ns <= 1 || m->n <= 1) return 0;
+    thrust::host_vector<float3> hp(ns), hn(ns);
+    for (int i = 0; i < ns; i++) {
+        hp[i] = make_float3(sxyz[3 * i], sxyz[3 * i + 1], sxyz[3 * i + 2]);
+        hn[i] = make_float3(snrm[3 * i], snrm[3 * i + 1], snrm[3 * i + 2]);
+    }
+    thrust::device_vector<float3> dp = hp, dn = hn;
+    thrust::device_vector<int> drefs(refs, refs + R);
+    thrust::device_vector<unsigned int> hist((std::size_t)R * m->n * 64, 0u);
+    thrust::device_vector<unsigned long long> nv(1, 0ull);
+    modeb_vote_kernel<<<148 * 16, 256>>>(
+        thrust::raw_pointer_cast(dp.data()), thrust::raw_pointer_cast(dn.data()), ns,
+        thrust::raw_pointer_cast(drefs.data()), R, thrust::raw_pointer_cast(m->points.data()),
+        thrust::raw_pointer_cast(m->normals.data()), m->n, RAW_PTR(m->search_array.GetHashkeys()),
+        RAW_PTR(m->search_array.GetCounts()), RAW_PTR(m->search_array.GetFirstHashkeyIndices()),
+        RAW_PTR(m->search_array.GetHashkeyToDataMap()), m->search_array.GetHashkeys()->size(), m->d_dist,
+        thrust::raw_pointer_cast(hist.data()), thrust::raw_pointer_cast(nv.data()));
+    if (cudaDeviceSynchronize() != cudaSuccess) return -1;
+    if (num_votes_out) *num_votes_out = (unsigned long)nv[0];
+    thrust::host_vector<unsigned int> hh = hist;
+    // reference points in ascending s_r so that the codes come out sorted
+    std::vector<int> order(R);
+    for (int i = 0; i < R; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return refs[a] < refs[b]; });
+    long n = 0;
+    for (int pass = 0; pass < 2; pass++) {
+        long k = 0;
+        for (int oi = 0; oi < R; oi++) {
+            const int r = order[oi];
+            for (int mr = 0; mr < m->n; mr++)
+                for (unsigned int a = 0; a < 64; a++) {
+                    const unsigned int c = hh[((std::size_t)r * m->n + mr) * 64 + a];
+                    if (!c) continue;
+                    if (pass == 1) {
+                        codes_out[k] = (((unsigned long)(unsigned int)refs[r]) << 32) | ((unsigned long)mr << 6) | a;
+                        counts_out[k] = c;
+                    }
+                    k++;
+                }
+        }
+        n = k;
+        if (pass == 0 && (!codes_out || !counts_out || n > capacity)) break;
+    }
+    return n;
+}
+
 // Wall-clock-free timing hook for the "reference GPU" comparator: time of
 // Scene ctor + ppf_lookup (model prebuilt), in milliseconds, CUDA events.
 float ref_time_scene_lookup(void *hm, const float *xyz, const float *nrm, int n,

@@ -44,6 +44,8 @@ def lib():
         L.ref_vote_histogram.argtypes = [vp, vp, vp, vp, cl]
         L.ref_time_scene_lookup.restype = cf
         L.ref_time_scene_lookup.argtypes = [vp, vp, vp, ci, cu, cf]
+        L.ref_modeb_histogram.restype = cl
+        L.ref_modeb_histogram.argtypes = [vp, vp, vp, ci, vp, ci, vp, vp, cl, vp]
         # host shims
         L.refhost_hash.restype = cu
         L.refhost_hash.argtypes = [vp, ci]
@@ -144,6 +146,23 @@ class RefModel:
         if n:
             lib().ref_vote_histogram(self.h, scene.h, _p(codes), _p(counts), n)
         return codes, counts
+
+    def modeb_histogram(self, pts, nrm, refs):
+        """Oracle Mode B: every non-zero accumulator cell (code, count; ascending code) of the scene
+        reference points `refs` (indices into the scene cloud), computed by the reference's device functions
+        streamed over the scene -- for sizes the whole-kernel replay (Mode A) cannot hold.  Also returns the
+        number of votes cast."""
+        pts, nrm = _f32(pts), _f32(nrm)
+        refs = np.ascontiguousarray(refs, np.int32)
+        nv = np.zeros(1, np.uint64)
+        n = lib().ref_modeb_histogram(self.h, _p(pts), _p(nrm), len(pts), _p(refs), len(refs), None, None, 0, _p(nv))
+        if n < 0:
+            raise RuntimeError("ref_modeb_histogram: CUDA error")
+        codes = np.empty(n, np.uint64)
+        counts = np.empty(n, np.uint32)
+        if n:
+            lib().ref_modeb_histogram(self.h, _p(pts), _p(nrm), len(pts), _p(refs), len(refs), _p(codes), _p(counts), n, _p(nv))
+        return codes, counts, int(nv[0])
 
     def time_scene_lookup(self, pts, nrm, ref_df=1, thr=0.4):
         pts, nrm = _f32(pts), _f32(nrm)

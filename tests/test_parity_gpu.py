@@ -182,3 +182,46 @@ def test_config3_model_build_stress_5k():
     for name, a, b in zip(("hashkeys", "counts", "first", "map"), rt, t):
         assert a.shape == b.shape and (a == b).all(), name
     assert len(t[3]) == 25_000_000 and t[1][0] == 5000          # bucket 0 = the self pairs
+
+
+@pytest.mark.parametrize("tau", [0.0849, 0.0814, 0.0881])
+def test_far_cell_collision(tau):
+    """kernel.cu:460-501: ANY scene key equal to a model key votes -- also the key of a feature cell whose distance
+    bin lies beyond every model pair (kd >= K_d), when its 32-bit FNV collides with a model key.  For
+    make_model(300, seed=105) and these tau_d such cells exist and are geometrically reachable
+    (tools/find_far_collision.py): plant a scene pair in each and expect the reference's extra votes."""
+    import objective_slam_b200 as ppf
+    from objective_slam_b200 import operators, synth
+    from oracle import farcells, refgpu
+    mp, mn = synth.make_model(300, seed=105)
+    d = synth.d_dist_for(mp, tau)
+    sp, sn, _ = synth.make_scene(mp, mn, 500, seed=205)
+    m = ppf.Model(mp, mn, d)
+    hk, cnt, _, _ = m.table()
+    pm, _ = m.features()
+    K_d = int(np.nanmax(pm[..., 0]) / np.float32(d) + 0.5) + 1                 # one past the model's last distance bin
+    planted, expect = [], 0
+    for cell, key in farcells.far_collisions(hk, K_d, 4 * K_d, d):
+        pair = farcells.plant_pair(cell, d, origin=(3.0, 3.0 + 9.0 * len(planted), 3.0))
+        if pair is None:
+            continue
+        p1, n1, p2, n2 = [np.asarray(x, np.float32) for x in pair]
+        _, k = operators.discretized_pair_feature(p1, n1, p2, n2, d)
+        assert int(k[0]) == key, "the planted pair must land in the colliding far cell"
+        planted.append((p1, n1, p2, n2))
+        expect += int(cnt[np.searchsorted(hk, np.uint32(key))])
+    assert planted, "no reachable far-cell collision for this model / tau_d (see tools/find_far_collision.py)"
+    pp = np.concatenate([[p[0], p[2]] for p in planted]).astype(np.float32)
+    pn = np.concatenate([[p[1], p[3]] for p in planted]).astype(np.float32)
+    # the planted pairs alone: every vote comes through a far cell (the points are > K_d bins apart)
+    if len(pp) == 2:
+        r = refgpu.RefModel(mp, mn, d); s2 = refgpu.RefScene(pp, pn, d, 1)
+        assert r.lookup(s2)["num_nonunique_votes"] >= expect > 0
+        q = m.ppf_lookup(ppf.Scene(pp, pn, d, 1))
+        assert q.num_nonunique_votes == r.lookup(s2)["num_nonunique_votes"]
+        compare_all(mp, mn, pp, pn, d, 1)
+    # inside a cluttered scene: every accumulator cell, survivor, pose equal to the reference's
+    sp2, sn2 = np.concatenate([sp, pp]), np.concatenate([sn, pn])
+    r, q = compare_all(mp, mn, sp2, sn2, d, 1)
+    base = ppf.Model(mp, mn, d).ppf_lookup(ppf.Scene(sp, sn, d, 1))
+    assert q.num_nonunique_votes >= base.num_nonunique_votes + expect
