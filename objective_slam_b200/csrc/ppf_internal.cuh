@@ -119,6 +119,8 @@ struct VoteResult {                           // device buffers of one ppf_looku
     size_t sched_cap = 0;
     uint32_t *acc_scratch = nullptr;          // accumulators of a dense scene's segments (ppf_vote_grouped.cu)
     size_t acc_scratch_cap = 0;
+    uint2 *replay = nullptr;                  // deferred exact votes, [CTAs][cap] (ppf_vote_grouped.cu)
+    size_t replay_cap = 0;
     // survivors, ordered (count desc, code asc) -- model.cu:155-170
     size_t K = 0;
     unsigned long long *codes = nullptr;

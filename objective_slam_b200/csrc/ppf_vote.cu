@@ -65,6 +65,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel(const VoteArgs a) {
     VoteCtx ctx;
     ctx.map = a.map; ctx.mfy = a.mfy; ctx.mfz = a.mfz; ctx.mpos = a.mpos; ctx.spos = a.spos;
     ctx.nm = a.nm; ctx.chunk_base = chunk_base; ctx.stride = S; ctx.acc = acc;
+    ctx.acc_addr = 0; ctx.opaque_zero = 0; ctx.rq = nullptr; ctx.rq_cap = 0; ctx.rq_count = nullptr;   // exact path inline
     unsigned long long my_votes = 0;
     uint32_t my_exact = 0;
 
@@ -277,6 +278,7 @@ static int ensure(void **p, size_t bytes) {
 
 void vote_result_free(VoteResult &r) {
     pooled_free(r.cand_codes); pooled_free(r.cand_counts); pooled_free(r.scalars); pooled_free(r.votes_total); pooled_free(r.sched); pooled_free(r.acc_scratch);
+    pooled_free(r.replay);
     pooled_free(r.codes); pooled_free(r.counts); pooled_free(r.transformations); pooled_free(r.weighted);
     pooled_free(r.trans); pooled_free(r.rots); pooled_free(r.scores);
     r.ws.release();
@@ -346,7 +348,8 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
         a.cell2bucket = m.cell2bucket; a.ranges = m.ranges; a.entries = m.entries; a.map = m.map;
         a.n_chunks = m.n_chunks; a.chunk_rows = m.chunk_rows;
-        a.queue_cap = 0; a.sched = nullptr; a.acc_scratch = nullptr;
+        a.queue_cap = 0; a.sched = nullptr; a.acc_scratch = nullptr; a.opaque_zero = 0;
+        a.replay = nullptr; a.replay_cap = 0;
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;
         a.cand_codes = r.cand_codes; a.cand_counts = r.cand_counts; a.cand_cap = (uint32_t)r.cand_cap;
         a.scalars = r.scalars; a.totals = r.votes_total;
@@ -371,6 +374,14 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
                 r.acc_scratch_cap = words;
             }
             a.acc_scratch = r.acc_scratch;
+            const size_t rq_words = (size_t)vote_grouped_ctas() * vote_grouped_replay_cap();
+            if (r.replay_cap < rq_words) {
+                pooled_free(r.replay); r.replay = nullptr; r.replay_cap = 0;
+                PPF_CUDA_TRY(pooled_malloc(&r.replay, rq_words * sizeof(uint2)));
+                r.replay_cap = rq_words;
+            }
+            a.replay = getenv("PPF_B200_INLINE_EXACT") ? nullptr : r.replay;
+            a.replay_cap = (uint32_t)vote_grouped_replay_cap();
             int rc = vote_grouped_launch(a, R);
             if (rc) return rc;
         } else if (smem > 113 * 1024) {

@@ -31,8 +31,11 @@ struct VoteArgs {
     // grouped kernel only: hit queue capacity (records); work counters: sched[0] = next reference point,
     // sched[1 + r] = next chunk of reference point r (zeroed before the launch)
     int queue_cap;
+    uint32_t opaque_zero;                         // always 0; a third add operand the compilers cannot fold (see vote_grouped)
     uint32_t *sched;
     uint32_t *acc_scratch;                        // [CTAs][n_chunks][31 x S]: accumulators parked between scene segments
+    uint2 *replay;                                // [CTAs][replay_cap]: deferred exact votes (nullptr: inline)
+    uint32_t replay_cap;
     // output
     float thr;
     int emit_all;                                 // 1: emit every non-zero cell (vote histogram)
@@ -76,6 +79,12 @@ struct VoteCtx {
     int nm, chunk_base, stride;
     uint32_t *acc;
     uint32_t acc_addr;                            // acc as a shared-window address (grouped kernel)
+    uint32_t opaque_zero;
+    // deferred exact votes (grouped kernel): records (table position, scene point) parked in global memory and
+    // replayed by the whole CTA at the end of the chunk; rq == nullptr: the exact path runs inline
+    uint2 *rq;
+    uint32_t rq_cap;
+    uint32_t *rq_count;                           // shared-memory counter
 };
 
 __device__ __forceinline__ void red_shared_inc(uint32_t addr) {
@@ -108,6 +117,32 @@ static __device__ __noinline__ uint32_t exact_vote_index(const VoteCtx &c, const
     return alpha_bin_exact(uy, uz, vy, vz) * (uint32_t)c.stride + loc;
 }
 
+// Same from the table position alone (the row comes from the pair the map names): replay of a deferred exact vote.
+static __device__ __forceinline__ uint32_t exact_vote_index_at(const VoteCtx &c, const FrameYZ &FS, uint32_t s_i, uint32_t pos) {
+    const uint32_t pidx = __ldg(c.map + pos);
+    const int m_r = (int)(pidx / (uint32_t)c.nm);
+    const int m_i = (int)(pidx - (uint32_t)m_r * (uint32_t)c.nm);
+    const FrameYZ FM = load_frame(c.mfy, c.mfz, m_r);
+    const float4 mi = __ldg(c.mpos + m_i);
+    const float4 si = __ldg(c.spos + s_i);
+    float uy, uz, vy, vz;
+    frame_apply_yz(FM, mi.x, mi.y, mi.z, uy, uz);
+    frame_apply_yz(FS, si.x, si.y, si.z, vy, vz);
+    return alpha_bin_exact(uy, uz, vy, vz) * (uint32_t)c.stride + (uint32_t)(m_r - c.chunk_base);
+}
+
+// +1 on the EXACT cell of one vote.  The exact path is a chain of dependent global loads (map -> frames -> points)
+// run by one lane while the other 31 wait: 12% of the grouped kernel's stall samples for 1.35e-4 of the votes.  With
+// a replay queue the lane only parks (position, scene point); the CTA replays the records densely (32 lanes busy,
+// latencies overlapped) before the chunk's accumulator is read.  Queue full -> inline, as before.
+__device__ __forceinline__ void exact_vote(const VoteCtx &c, const FrameYZ &FS, uint32_t s_i, uint32_t entry, uint32_t pos) {
+    if (c.rq) {
+        const uint32_t slot = atomicAdd(c.rq_count, 1u);
+        if (slot < c.rq_cap) { c.rq[slot] = make_uint2(pos, s_i); return; }
+    }
+    atomicAdd(&c.acc[exact_vote_index(c, FS, s_i, entry, pos)], 1u);
+}
+
 // The hot loop votes OPTIMISTICALLY: every entry of a batch adds 1 to the cell its fast alpha bin
 // names (always a valid cell), the guard-band margins are min-reduced and the slow flags OR-ed across
 // the batch (one VIADDMNMX and half a LOP3 per vote), and only when a batch contains a vote whose fast
@@ -120,7 +155,7 @@ __device__ __forceinline__ void repair_vote(const VoteCtx &c, const FrameYZ &FS,
     uint32_t bin;
     if (alpha_bin_margin(hit_ones, entry, bin) >= kGuardSpan || (entry & kSlowBit)) {
         atomicSub(&c.acc[bin * (uint32_t)c.stride + (entry & kLocMask)], 1u);
-        atomicAdd(&c.acc[exact_vote_index(c, FS, s_i, entry, pos)], 1u);
+        exact_vote(c, FS, s_i, entry, pos);
         n_exact++;
     }
 }
@@ -228,5 +263,6 @@ bool   vote_grouped_supported(const ModelTable &m, int ns);
 int    vote_grouped_launch(VoteArgs a, int ref_count);
 int    vote_grouped_ctas();
 size_t vote_grouped_scratch_words(const ModelTable &m);
+size_t vote_grouped_replay_cap();
 
 }  // namespace ppf

@@ -30,26 +30,33 @@
 namespace ppf {
 
 constexpr uint32_t kGTile       = kHitQueue;        // scene points per phase-1 tile (the scene's tile AABBs)
-constexpr int      kGStage      = 64;               // entries staged per warp per block (two per lane)
+#ifndef PPF_GSTAGE
+#define PPF_GSTAGE 64
+#endif
+constexpr int      kGStage      = PPF_GSTAGE;       // staging slots per warp: 64 entries per block (two per lane) [+ group padding]
 constexpr uint32_t kGGrabVotes  = 32768;            // votes per scheduler ticket of a grouped piece (8192: 699 ms, 16384: 685, 32768: 679, 65536: 689 on configs[1])
 constexpr int      kGItemsMax   = 16;               // queue records per thread in the ticket scan
 // hit record: [bucket : 20 | (theta_v + half) : 20 | slow : 1 | stored scene index : 23]
 constexpr int      kGBucketShift = 44;
 constexpr int      kGThetaShift  = 24;
 constexpr uint32_t kGIndexMask   = (1u << 23) - 1u;
+#ifndef PPF_GTHREADS
+#define PPF_GTHREADS 1024
+#endif
+constexpr int      kGThreads     = PPF_GTHREADS;     // threads per CTA of the grouped kernel
 constexpr size_t   kGSmemMax     = 227 * 1024 - 512;  // opt-in maximum minus the kernel's static shared memory
 
 static size_t acc_bytes(int chunk_rows) { return ((size_t)kNAlphaBins * acc_stride(chunk_rows) * 4 + 15) & ~(size_t)15; }
 
 // Largest hit queue (multiple of 1024 records, 12 B each) that fits next to the accumulator.
 int vote_grouped_queue_cap(int chunk_rows) {
-    const size_t fixed = (size_t)32 * kGStage * sizeof(uint2) + acc_bytes(chunk_rows);
+    const size_t fixed = (size_t)(kGThreads / 32) * kGStage * sizeof(uint2) + acc_bytes(chunk_rows);
     if (fixed + 1024 * 12 > kGSmemMax) return 0;
     const size_t q = (kGSmemMax - fixed) / 12 / 1024 * 1024;
     return (int)std::min<size_t>(q, (size_t)kGItemsMax * 1024);
 }
 size_t vote_grouped_smem(int chunk_rows) {
-    return (size_t)vote_grouped_queue_cap(chunk_rows) * 12 + (size_t)32 * kGStage * sizeof(uint2) + acc_bytes(chunk_rows);
+    return (size_t)vote_grouped_queue_cap(chunk_rows) * 12 + (size_t)(kGThreads / 32) * kGStage * sizeof(uint2) + acc_bytes(chunk_rows);
 }
 bool vote_grouped_supported(const ModelTable &m, int ns) {
     return m.chunk_rows <= kGroupedMaxRows && m.U < (1u << 20) && ns <= (int)kGIndexMask &&
@@ -81,6 +88,15 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
     const uint32_t lhg = code + 1u;                 // log2(HG)
     const uint32_t HG = 1u << lhg, EG = 32u >> lhg, K = 2u * HG;
     const uint32_t g = (uint32_t)lane >> lhg;
+    // Shared-memory banks.  Group g's K staged pairs start at g * KP (uint2 units).  KP = K puts the groups of small
+    // pieces at a byte stride of 16 HG = 128 / 64 B: the 4 (HG = 8) or 8 (HG = 4) groups of one LDS.128 then read the
+    // same banks (ncu: 21% of the LDS wavefronts were bank conflicts) -- one 16 B pad per group spreads them over
+    // distinct banks.  And the lane that STAGES slot (g, m) is lane g HG + m, so that the 8 lanes of a quarter warp
+    // write one contiguous 128 B run (the old mapping, lane = entry index, had them 64 - 256 B apart: STS.128 took
+    // 11.2 wavefronts instead of 4).
+    const uint32_t KP = K + ((kGStage >= 80 && HG <= 8u) ? 2u : 0u);
+    const uint32_t m_slot = (uint32_t)lane & (HG - 1u);
+    const uint32_t jl = m_slot * EG + g;            // this lane loads entries jl and jl + 32 of every block
     const unsigned long long rec = gc.queue[i0 + ((uint32_t)lane & (HG - 1u))];
     const uint32_t hit_ones = ((uint32_t)(rec >> kGThetaShift) << kThetaShift) | kLowOnes;
     const bool hit_slow = ((uint32_t)rec >> 23) & 1u;
@@ -89,37 +105,43 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
     // Loop invariants that ptxas would otherwise REMATERIALISE in every block (shared-window base via S2UR +
     // ULEA + LDC + LEA ..., lane via S2R + LOP3: ~20 of the ~60 staging instructions per block): an empty asm
     // makes the value opaque, so it stays in a register for the duration of the ticket.
-    uint32_t trash = gc.trash_addr, acc_base = ctx.acc_addr, l32 = (uint32_t)lane;
+    uint32_t trash = gc.trash_addr, acc_base = ctx.acc_addr, l32 = jl;
     asm volatile("" : "+r"(trash), "+r"(acc_base), "+r"(l32));
-    // this lane loads entries l and l + 32 of a block: group l % EG, positions 2 (l / EG) and 2 (l / EG) + 1
-    uint4 *my_slot = reinterpret_cast<uint4 *>(gc.stage + (((uint32_t)lane & (EG - 1u)) * K + 2u * ((uint32_t)lane / EG)));
-    const uint2 *grp = gc.stage + g * K;
+    // this lane loads entries jl and jl + 32 of a block: group g, positions 2 m_slot and 2 m_slot + 1
+    uint4 *my_slot = reinterpret_cast<uint4 *>(gc.stage + (g * KP + 2u * m_slot));
+    const uint2 *grp = gc.stage + g * KP;
     const uint4 *src = reinterpret_cast<const uint4 *>(grp);
-    const uint32_t *__restrict__ ent = entries + pos_grab + lane;
+    const uint32_t *__restrict__ ent = entries + pos_grab + jl;
 
     // exact recount of the staged positions [p0, p1) of this lane's group (rare)
     auto repair = [&](uint32_t p0, uint32_t p1, uint32_t blk_pos) {
 #pragma unroll 1
         for (uint32_t p = p0; p < p1; p++) {
-            const uint2 r = grp[p];
+            uint2 r = grp[p];
+            r.x = 0u - r.x;                                    // staged negated
             uint32_t bin;
             const uint32_t margin = alpha_bin_margin(hit_ones, r.x, bin);
             if (r.y != trash && (margin >= kGuardSpan || (r.x & kSlowBit) || hit_slow)) {
                 const uint32_t j = (p & 1u) * 32u + (p >> 1) * EG + g;          // entry index within the block
                 atomicSub(&ctx.acc[bin * (uint32_t)ctx.stride + (r.x & kLocMask)], 1u);
-                atomicAdd(&ctx.acc[exact_vote_index(ctx, FS, s_i, r.x, blk_pos + j)], 1u);
+                exact_vote(ctx, FS, s_i, r.x, blk_pos + j);
                 n_exact++;
             }
         }
     };
+    // hit - entry is computed as max(hit + (-entry), zero) with the entries staged NEGATED and `zero` a kernel argument
+    // the compilers cannot fold: add + max fuse into one VIADDMNMX on the ALU pipe.  A plain subtraction becomes
+    // IMAD.IADD, i.e. a third op per vote (with the IMAD.WIDE and the address IMAD) on the FMA-heavy pipe, which ncu
+    // shows 68% busy over the whole kernel (math-pipe throttle the #3 stall reason) against 36% for the ALU pipe.
+    const uint32_t zero = ctx.opaque_zero;
     auto vote2 = [&](const uint4 q, uint32_t &worst) {
         {
-            const unsigned long long p = (unsigned long long)(hit_ones - q.x) * (unsigned long long)kNAngle;
+            const unsigned long long p = (unsigned long long)max(hit_ones + q.x, zero) * (unsigned long long)kNAngle;
             worst = max(worst, (uint32_t)p - kGuardLoA);
             red_shared_inc((uint32_t)(p >> 32) * S4 + q.y);
         }
         {
-            const unsigned long long p = (unsigned long long)(hit_ones - q.z) * (unsigned long long)kNAngle;
+            const unsigned long long p = (unsigned long long)max(hit_ones + q.z, zero) * (unsigned long long)kNAngle;
             worst = max(worst, (uint32_t)p - kGuardLoA);
             red_shared_inc((uint32_t)(p >> 32) * S4 + q.w);
         }
@@ -147,7 +169,7 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
             slow = ((c0 | c1) & kSlowBit) != 0u;
         }
         __syncwarp();
-        *my_slot = make_uint4(c0, a0, c1, a1);
+        *my_slot = make_uint4(0u - c0, a0, 0u - c1, a1);     // staged as (-entry, row address)
         const unsigned slowmask = __ballot_sync(0xffffffffu, slow);
         __syncwarp();
         const uint32_t worst0 = (hit_slow || slowmask) ? 0xFFFFFFFFu : 0u;
@@ -186,12 +208,12 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
             for (uint32_t k = 0; k < pairs; k++) {
                 const uint4 q = src[k];
                 {
-                    const unsigned long long p = (unsigned long long)(hit_ones - q.x) * (unsigned long long)kNAngle;
+                    const unsigned long long p = (unsigned long long)(hit_ones + q.x) * (unsigned long long)kNAngle;
                     if (q.y != trash) worst = max(worst, (uint32_t)p - kGuardLoA);
                     red_shared_inc((uint32_t)(p >> 32) * S4 + q.y);
                 }
                 {
-                    const unsigned long long p = (unsigned long long)(hit_ones - q.z) * (unsigned long long)kNAngle;
+                    const unsigned long long p = (unsigned long long)(hit_ones + q.z) * (unsigned long long)kNAngle;
                     if (q.w != trash) worst = max(worst, (uint32_t)p - kGuardLoA);
                     red_shared_inc((uint32_t)(p >> 32) * S4 + q.w);
                 }
@@ -245,8 +267,8 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     unsigned long long *queue = reinterpret_cast<unsigned long long *>(smem_raw);        // [Q] hit records
     uint32_t *gend = reinterpret_cast<uint32_t *>(queue + Q);                             // [Q] ticket table
     uint2 *stage_all = reinterpret_cast<uint2 *>(gend + Q);                               // [32 warps][kGStage]
-    uint32_t *acc = reinterpret_cast<uint32_t *>(stage_all + 32 * kGStage);               // [31][S] vote counters
-    __shared__ uint32_t s_nhits, s_ticket, s_total, s_exact;
+    uint32_t *acc = reinterpret_cast<uint32_t *>(stage_all + (THREADS / 32) * kGStage);   // [31][S] vote counters
+    __shared__ uint32_t s_nhits, s_ticket, s_total, s_exact, s_rq;
     __shared__ uint32_t s_red[32];
     __shared__ unsigned long long s_votes;
     // reference point and its frame: only phase 1 and the exact-alpha path read them, so they live in
@@ -266,11 +288,14 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     ctx.map = a.map; ctx.mfy = a.mfy; ctx.mfz = a.mfz; ctx.mpos = a.mpos; ctx.spos = a.spos;
     ctx.nm = a.nm; ctx.chunk_base = 0; ctx.stride = S; ctx.acc = acc;
     ctx.acc_addr = (uint32_t)__cvta_generic_to_shared(acc);
+    ctx.opaque_zero = a.opaque_zero;
+    ctx.rq = a.replay ? a.replay + (size_t)blockIdx.x * a.replay_cap : nullptr;
+    ctx.rq_cap = a.replay_cap; ctx.rq_count = &s_rq;
     GroupCtx gc;
     gc.queue = queue; gc.stage = stage_all + warp * kGStage; gc.trash_addr = ctx.acc_addr + (uint32_t)C * 4u;
     unsigned long long my_votes = 0;
     uint32_t my_exact = 0;
-    const int items = (int)(Q / THREADS);
+    const int items = (int)((Q + THREADS - 1) / THREADS);
     unsigned long long heads = 0;                   // 4 bits per owned queue record: head << 3 | piece code
     __syncthreads();
 
@@ -386,7 +411,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             if (lane >= o) incl += t;
         }
         if (lane == 31) s_red[warp] = incl;
-        if (tid == 0) s_ticket = 0;
+        if (tid == 0) { s_ticket = 0; s_rq = 0; }
         __syncthreads();
         if (warp == 0) {
             const uint32_t x = lane < THREADS / 32 ? s_red[lane] : 0u;
@@ -431,6 +456,15 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             }
         }
         __syncthreads();
+        // replay of the deferred exact votes of this chunk: one record per thread, all lanes busy
+        if (ctx.rq) {
+            const uint32_t nr = min(s_rq, ctx.rq_cap);
+            for (uint32_t i = tid; i < nr; i += THREADS) {
+                const uint2 r = ctx.rq[i];
+                atomicAdd(&ctx.acc[exact_vote_index_at(ctx, FS, r.y, r.x)], 1u);
+            }
+            __syncthreads();
+        }
     };
 
     // ---- jobs.  Persistent CTAs draw reference points from sched[0]; the chunks of reference point r are
@@ -627,6 +661,8 @@ int vote_grouped_ctas() {
     if (const char *e = getenv("PPF_B200_VOTE_CTAS")) n_sm = std::max(1, atoi(e));
     return n_sm;
 }
+// deferred exact votes: records per CTA (8 B each); ~1.35e-4 of the votes of one (reference point, chunk) pass
+size_t vote_grouped_replay_cap() { return 16384; }
 size_t vote_grouped_scratch_words(const ModelTable &m) {
     return (size_t)vote_grouped_ctas() * m.n_chunks * ((size_t)kNAlphaBins * acc_stride(m.chunk_rows));
 }
@@ -641,11 +677,11 @@ int vote_grouped_launch(VoteArgs a, int ref_count) {
     // work from the counters in a.sched (zeroed by the caller)
     const long long grid = vote_grouped_ctas();
     const size_t smem = vote_grouped_smem(a.chunk_rows);
-    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<1024, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vote_kernel_grouped<1024, false><<<(unsigned)grid, 1024, smem>>>(a);
+    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vote_kernel_grouped<kGThreads, false><<<(unsigned)grid, kGThreads, smem>>>(a);
     // reference points whose hits did not fit the queue (none on sparse scenes: the kernel then exits at once)
-    vote_kernel_grouped<1024, true><<<(unsigned)grid, 1024, smem>>>(a);
+    vote_kernel_grouped<kGThreads, true><<<(unsigned)grid, kGThreads, smem>>>(a);
     count_launch(2);
     return PPF_OK;
 }
