@@ -57,6 +57,7 @@ enum { PPF_MEM_HOST = 0, PPF_MEM_DEVICE = 1 };
 typedef struct ppf_scene ppf_scene_t;
 typedef struct ppf_model ppf_model_t;
 typedef struct ppf_lookup ppf_lookup_t;
+typedef struct ppf_comm ppf_comm_t;      /* the ranks of a sharded recognition (one GPU each) */
 
 const char *ppf_last_error(void);
 const char *ppf_version(void);
@@ -211,12 +212,45 @@ int ppf_vote_histogram_shard(const ppf_model_t *model, const ppf_scene_t *scene,
                              unsigned ref_point_downsample_factor, int shard_rank, int shard_count,
                              uint64_t *codes_out, uint32_t *counts_out, size_t capacity, size_t *n_out);
 
-/* ---- The drop-in boundary -------------------------------------------------------- */
 typedef struct ppf_cloud {
     const float *xyz; int xyz_stride;
     const float *nrm; int nrm_stride;
     int n;
 } ppf_cloud_t;
+
+/* ---- Multi-GPU: scene reference points sharded over the ranks of one node --------------
+ * One host process (or host thread) per GPU, the rank's device current.  Voting needs no data-path collective (a
+ * scene reference point owns its accumulator: the high 32 bits of a vote code are s_r, model.h:61-63); what the
+ * reference does GLOBALLY -- the threshold count > thr * max and the clustering of the surviving votes,
+ * model.cu:160-170, 202-244 -- is done on the merged survivor list: all_reduce(MAX) of one u32, all_gather of
+ * the survivor records, all_reduce(SUM) of the clustering scores of interleaved pose slices.  The collectives are
+ * NCCL's (libnccl.so.2 is dlopen()ed on first use: no link-time dependency); the model table is replicated.
+ *
+ * A communicator is made from an NCCL unique id (rank 0 calls ppf_comm_unique_id and ships the PPF_COMM_ID_BYTES
+ * bytes to the other ranks by any means, then every rank calls ppf_comm_create_nccl), or wraps an ncclComm_t the
+ * host already owns.  ppf_comm_create_local makes `world` communicators for `world` host THREADS of one process on
+ * one GPU (rendezvous through host memory): the single-GPU test vehicle of this path. */
+#define PPF_COMM_ID_BYTES 128
+int ppf_comm_unique_id(void *id_out);
+int ppf_comm_create_nccl(const void *id, int rank, int world, ppf_comm_t **out);
+int ppf_comm_wrap_nccl(void *nccl_comm, int rank, int world, ppf_comm_t **out);
+int ppf_comm_create_local(int world, ppf_comm_t **out_array);
+int ppf_comm_rank(const ppf_comm_t *comm);
+int ppf_comm_size(const ppf_comm_t *comm);
+void ppf_comm_destroy(ppf_comm_t *comm);
+/* Model::ppf_lookup over the ranks of `comm`: every rank passes the same model (replicated) and the same scene and
+ * gets the same survivors, poses, scores and winner as ppf_model_lookup on one GPU (bit for bit; with
+ * use_averaged_clusters the clustering runs replicated).  The stats' vote / pair counters are the rank's own. */
+int ppf_model_lookup_sharded(const ppf_model_t *model, const ppf_scene_t *scene,
+                             unsigned ref_point_downsample_factor, ppf_comm_t *comm, ppf_lookup_t *lk);
+/* ppf_registration called by every rank of `comm` with the same arguments: same poses on every rank. */
+int ppf_registration_sharded(const ppf_cloud_t *scene_clouds, int num_scenes, const ppf_cloud_t *model_clouds,
+                             int num_models, const float *model_d_dists,
+                             unsigned ref_point_downsample_factor, float vote_count_threshold,
+                             int cpu_clustering, int use_l1_norm, int use_averaged_clusters,
+                             ppf_comm_t *comm, float *poses_out, int *status_out);
+
+/* ---- The drop-in boundary -------------------------------------------------------- */
 
 /* ppf_registration (ppf.h:9-15): for every scene i and model j build Scene(scene_i, d_dist_j,
  * df) and Model(model_j, d_dist_j, ...), run ppf_lookup and write the best model->scene pose to

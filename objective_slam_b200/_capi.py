@@ -28,6 +28,8 @@ EXPORTS = [
     "ppf_lookup_poses", "ppf_lookup_cluster", "ppf_lookup_cluster_shard", "ppf_lookup_copy_scores",
     "ppf_lookup_set_scores", "ppf_lookup_cluster_finish", "ppf_lookup_cluster_cpu", "ppf_lookup_get_stats",
     "ppf_lookup_get", "ppf_vote_histogram", "ppf_vote_histogram_shard", "ppf_registration",
+    "ppf_comm_unique_id", "ppf_comm_create_nccl", "ppf_comm_wrap_nccl", "ppf_comm_create_local", "ppf_comm_rank",
+    "ppf_comm_size", "ppf_comm_destroy", "ppf_model_lookup_sharded", "ppf_registration_sharded",
 ]
 
 
@@ -116,6 +118,16 @@ def _load():
     L.ppf_vote_histogram.argtypes = [vp, vp, cu, vp, vp, sz, P(sz)]
     L.ppf_vote_histogram_shard.argtypes = [vp, vp, cu, ci, ci, vp, vp, sz, P(sz)]
     L.ppf_registration.argtypes = [P(CloudDesc), ci, P(CloudDesc), ci, vp, cu, cf, ci, ci, ci, ci, vp, vp, vp]
+    L.ppf_comm_unique_id.argtypes = [vp]
+    L.ppf_comm_create_nccl.argtypes = [vp, ci, ci, P(vp)]
+    L.ppf_comm_wrap_nccl.argtypes = [vp, ci, ci, P(vp)]
+    L.ppf_comm_create_local.argtypes = [ci, P(vp)]
+    L.ppf_comm_rank.argtypes = [vp]
+    L.ppf_comm_size.argtypes = [vp]
+    L.ppf_comm_destroy.argtypes = [vp]
+    L.ppf_comm_destroy.restype = None
+    L.ppf_model_lookup_sharded.argtypes = [vp, vp, cu, vp, vp]
+    L.ppf_registration_sharded.argtypes = [P(CloudDesc), ci, P(CloudDesc), ci, vp, cu, cf, ci, ci, ci, vp, vp, vp]
     return L
 
 

@@ -15,6 +15,23 @@ static thread_local std::string g_last_error;
 void set_last_error(const std::string &msg) { g_last_error = msg; }
 static std::atomic<unsigned long long> g_kernel_launches{0};
 void count_launch(int n) { g_kernel_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+cudaStream_t cur_stream() {
+    constexpr int kMaxDev = 64;
+    static thread_local cudaStream_t streams[kMaxDev] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDev) return cudaStreamPerThread;
+    if (!streams[dev] && cudaStreamCreateWithFlags(&streams[dev], cudaStreamNonBlocking) != cudaSuccess) {
+        streams[dev] = nullptr;
+        return cudaStreamPerThread;
+    }
+    return streams[dev];
+}
+cudaError_t memcpy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+    cudaStream_t s = cur_stream();
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, s);
+    return e != cudaSuccess ? e : cudaStreamSynchronize(s);
+}
 }  // namespace ppf
 
 using namespace ppf;
@@ -38,8 +55,8 @@ int read_vote_scalars(ppf_lookup *lk) {
     uint32_t h[4] = {0, 0, 0, 0};
     unsigned long long t[2] = {0, 0};
     if (lk->res.scalars) {
-        PPF_CUDA_TRY(cudaMemcpy(h, lk->res.scalars, sizeof(h), cudaMemcpyDeviceToHost));
-        PPF_CUDA_TRY(cudaMemcpy(t, lk->res.votes_total, sizeof(t), cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(memcpy_sync(h, lk->res.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(memcpy_sync(t, lk->res.votes_total, sizeof(t), cudaMemcpyDeviceToHost));
     }
     lk->stats.max_vote_count = h[1];
     lk->stats.num_exact_alpha = h[3];
@@ -189,9 +206,9 @@ int ppf_lookup_vote(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, int
     PPF_CHECK_ARG(m && s && lk, "vote: NULL handle");
     std::memset(&lk->stats, 0, sizeof(lk->stats));
     unsigned long long pairs = 0;
-    cudaEventRecord(lk->ev[0], 0);
+    cudaEventRecord(lk->ev[0], cur_stream());
     int rc = vote_run(m->table, s->cloud, df, shard_rank, shard_count, 0, lk->res, &pairs, &lk->kernel_launches);
-    cudaEventRecord(lk->ev[1], 0);
+    cudaEventRecord(lk->ev[1], cur_stream());
     if (rc) return rc;
     PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[1]));
     cudaEventElapsedTime(&lk->stats.ms_vote, lk->ev[0], lk->ev[1]);
@@ -207,9 +224,9 @@ int ppf_lookup_local_max(const ppf_lookup_t *lk, uint32_t *max_count) {
 
 int ppf_lookup_finalize(const ppf_model_t *m, uint32_t global_max, ppf_lookup_t *lk) {
     PPF_CHECK_ARG(m && lk, "finalize: NULL handle");
-    cudaEventRecord(lk->ev[1], 0);
+    cudaEventRecord(lk->ev[1], cur_stream());
     int rc = vote_finalize(m->table, global_max, 0, lk->res);
-    cudaEventRecord(lk->ev[2], 0);
+    cudaEventRecord(lk->ev[2], cur_stream());
     if (rc) return rc;
     PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[2]));
     cudaEventElapsedTime(&lk->stats.ms_finalize, lk->ev[1], lk->ev[2]);
@@ -229,8 +246,8 @@ int ppf_lookup_survivors(const ppf_lookup_t *lk, size_t *K, const uint64_t **cod
 int ppf_lookup_copy_survivors(const ppf_lookup_t *lk, uint64_t *codes_dst_dev, uint32_t *counts_dst_dev) {
     PPF_CHECK_ARG(lk && (lk->res.K == 0 || (codes_dst_dev && counts_dst_dev)), "copy_survivors: NULL argument");
     if (lk->res.K == 0) return PPF_OK;
-    PPF_CUDA_TRY(cudaMemcpy(codes_dst_dev, lk->res.codes, lk->res.K * 8, cudaMemcpyDeviceToDevice));
-    PPF_CUDA_TRY(cudaMemcpy(counts_dst_dev, lk->res.counts, lk->res.K * 4, cudaMemcpyDeviceToDevice));
+    PPF_CUDA_TRY(memcpy_sync(codes_dst_dev, lk->res.codes, lk->res.K * 8, cudaMemcpyDeviceToDevice));
+    PPF_CUDA_TRY(memcpy_sync(counts_dst_dev, lk->res.counts, lk->res.K * 4, cudaMemcpyDeviceToDevice));
     return PPF_OK;
 }
 
@@ -242,8 +259,8 @@ int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const 
         if (rc0) return rc0;
         c = lk->res.ws.take<unsigned long long>(K);
         n = lk->res.ws.take<uint32_t>(K);
-        PPF_CUDA_TRY(cudaMemcpyAsync(c, codes_dev, K * 8, cudaMemcpyDeviceToDevice, 0));
-        PPF_CUDA_TRY(cudaMemcpyAsync(n, counts_dev, K * 4, cudaMemcpyDeviceToDevice, 0));
+        PPF_CUDA_TRY(cudaMemcpyAsync(c, codes_dev, K * 8, cudaMemcpyDeviceToDevice, cur_stream()));
+        PPF_CUDA_TRY(cudaMemcpyAsync(n, counts_dev, K * 4, cudaMemcpyDeviceToDevice, cur_stream()));
     }
     int rc = order_survivors(lk->res, K, c, n);
     lk->stats.num_top_votes = (uint32_t)lk->res.K;
@@ -252,14 +269,14 @@ int ppf_lookup_set_survivors(ppf_lookup_t *lk, const uint64_t *codes_dev, const 
 
 int ppf_lookup_poses(const ppf_model_t *m, const ppf_scene_t *s, ppf_lookup_t *lk) {
     PPF_CHECK_ARG(m && s && lk, "poses: NULL handle");
-    cudaEventRecord(lk->ev[2], 0);
+    cudaEventRecord(lk->ev[2], cur_stream());
     return poses_run(m->table, s->cloud, lk->res);
 }
 
 int ppf_lookup_cluster(const ppf_model_t *m, ppf_lookup_t *lk) {
     PPF_CHECK_ARG(m && lk, "cluster: NULL handle");
     int rc = cluster_run(m->table, lk->res);
-    cudaEventRecord(lk->ev[3], 0);
+    cudaEventRecord(lk->ev[3], cur_stream());
     if (rc) return rc;
     PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[3]));
     cudaEventElapsedTime(&lk->stats.ms_pose_cluster, lk->ev[2], lk->ev[3]);
@@ -278,18 +295,18 @@ int ppf_lookup_cluster_shard(const ppf_model_t *m, ppf_lookup_t *lk, int shard, 
 }
 int ppf_lookup_copy_scores(const ppf_lookup_t *lk, float *scores_dst_dev) {
     PPF_CHECK_ARG(lk && (lk->res.K == 0 || scores_dst_dev), "copy_scores: NULL argument");
-    if (lk->res.K) PPF_CUDA_TRY(cudaMemcpy(scores_dst_dev, lk->res.scores, lk->res.K * 4, cudaMemcpyDeviceToDevice));
+    if (lk->res.K) PPF_CUDA_TRY(memcpy_sync(scores_dst_dev, lk->res.scores, lk->res.K * 4, cudaMemcpyDeviceToDevice));
     return PPF_OK;
 }
 int ppf_lookup_set_scores(ppf_lookup_t *lk, const float *scores_src_dev) {
     PPF_CHECK_ARG(lk && (lk->res.K == 0 || scores_src_dev), "set_scores: NULL argument");
-    if (lk->res.K) PPF_CUDA_TRY(cudaMemcpy(lk->res.scores, scores_src_dev, lk->res.K * 4, cudaMemcpyDeviceToDevice));
+    if (lk->res.K) PPF_CUDA_TRY(memcpy_sync(lk->res.scores, scores_src_dev, lk->res.K * 4, cudaMemcpyDeviceToDevice));
     return PPF_OK;
 }
 int ppf_lookup_cluster_finish(ppf_lookup_t *lk) {
     PPF_CHECK_ARG(lk, "cluster_finish: NULL handle");
     int rc = cluster_finish(lk->res);
-    cudaEventRecord(lk->ev[3], 0);
+    cudaEventRecord(lk->ev[3], cur_stream());
     if (rc) return rc;
     PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[3]));
     cudaEventElapsedTime(&lk->stats.ms_pose_cluster, lk->ev[2], lk->ev[3]);
@@ -297,19 +314,41 @@ int ppf_lookup_cluster_finish(ppf_lookup_t *lk) {
     return PPF_OK;
 }
 
-// gpu_clustering = false: stop after the poses (the caller clusters on the host, Model::ppf_lookup with
+// Whole Model::ppf_lookup (model.cu:269-306) on the library's stream, alone or as rank comm->rank of comm->world
+// ranks that share the scene (reference points sharded, everything after the vote on the merged survivor list).
+// Host synchronisations: after the vote kernel (candidate overflow check), after the filter (K sizes the sorts), after
+// the count exchange (sharded only), and when the winner is read.
+// gpu_clustering = false: stop after the poses (the caller clusters on the host; Model::ppf_lookup with
 // cpu_clustering set never runs ClusterTransformations, model.cu:284-291)
-static int lookup_run(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk, bool gpu_clustering) {
-    int rc = ppf_lookup_vote(m, s, df, 0, 1, lk);
+static int lookup_run(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk, bool gpu_clustering,
+                      Comm *comm) {
+    PPF_CHECK_ARG(m && s && lk, "lookup: NULL handle");
+    const int rank = comm ? comm->rank : 0, world = comm ? comm->world : 1;
+    int rc = ppf_lookup_vote(m, s, df, rank, world, lk);
     if (rc) return rc;
-    if ((rc = ppf_lookup_finalize(m, lk->stats.max_vote_count, lk))) return rc;
-    if ((rc = ppf_lookup_poses(m, s, lk))) return rc;
-    if (gpu_clustering && (rc = ppf_lookup_cluster(m, lk))) return rc;
-    if (lk->stats.num_nonunique_votes == 0) { set_last_error("lookup: no scene pair matched the model"); return PPF_ERR_NO_VOTES; }
+    cudaEventRecord(lk->ev[1], cur_stream());
+    uint32_t gmax = 0;
+    if ((rc = vote_finalize_dist(m->table, comm, lk->res, &gmax))) return rc;
+    cudaEventRecord(lk->ev[2], cur_stream());
+    lk->stats.max_vote_count = gmax;
+    lk->stats.num_top_votes = (uint32_t)lk->res.K;
+    if ((rc = poses_run(m->table, s->cloud, lk->res))) return rc;
+    if (gpu_clustering) {
+        if ((rc = cluster_dist(m->table, comm, lk->res))) return rc;
+        lk->stats.max_idx = lk->res.max_idx;
+    }
+    cudaEventRecord(lk->ev[3], cur_stream());
+    PPF_CUDA_TRY(cudaEventSynchronize(lk->ev[3]));
+    cudaEventElapsedTime(&lk->stats.ms_finalize, lk->ev[1], lk->ev[2]);
+    cudaEventElapsedTime(&lk->stats.ms_pose_cluster, lk->ev[2], lk->ev[3]);
+    if (gmax == 0) { set_last_error("lookup: no scene pair matched the model"); return PPF_ERR_NO_VOTES; }
     return PPF_OK;
 }
 int ppf_model_lookup(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_lookup_t *lk) {
-    return lookup_run(m, s, df, lk, true);
+    return lookup_run(m, s, df, lk, true, nullptr);
+}
+int ppf_model_lookup_sharded(const ppf_model_t *m, const ppf_scene_t *s, unsigned df, ppf_comm_t *comm, ppf_lookup_t *lk) {
+    return lookup_run(m, s, df, lk, true, comm_impl(comm));
 }
 
 int ppf_lookup_get_stats(const ppf_lookup_t *lk, ppf_lookup_stats_t *stats) {
@@ -325,18 +364,18 @@ int ppf_lookup_get(const ppf_lookup_t *lk, uint64_t *votes, uint32_t *counts, fl
     size_t K = r.K;
     if (pose) std::memset(pose, 0, 16 * sizeof(float));
     if (K == 0) return PPF_OK;
-    if (votes) PPF_CUDA_TRY(cudaMemcpy(votes, r.codes, K * 8, cudaMemcpyDeviceToHost));
-    if (counts) PPF_CUDA_TRY(cudaMemcpy(counts, r.counts, K * 4, cudaMemcpyDeviceToHost));
-    if (transformations) PPF_CUDA_TRY(cudaMemcpy(transformations, r.transformations, K * 64, cudaMemcpyDeviceToHost));
-    if (weighted) PPF_CUDA_TRY(cudaMemcpy(weighted, r.weighted, K * 4, cudaMemcpyDeviceToHost));
-    if (trans) PPF_CUDA_TRY(cudaMemcpy(trans, r.trans, K * 12, cudaMemcpyDeviceToHost));
-    if (rots) PPF_CUDA_TRY(cudaMemcpy(rots, r.rots, K * 16, cudaMemcpyDeviceToHost));
-    if (scores) PPF_CUDA_TRY(cudaMemcpy(scores, r.scores, K * 4, cudaMemcpyDeviceToHost));
+    if (votes) PPF_CUDA_TRY(memcpy_sync(votes, r.codes, K * 8, cudaMemcpyDeviceToHost));
+    if (counts) PPF_CUDA_TRY(memcpy_sync(counts, r.counts, K * 4, cudaMemcpyDeviceToHost));
+    if (transformations) PPF_CUDA_TRY(memcpy_sync(transformations, r.transformations, K * 64, cudaMemcpyDeviceToHost));
+    if (weighted) PPF_CUDA_TRY(memcpy_sync(weighted, r.weighted, K * 4, cudaMemcpyDeviceToHost));
+    if (trans) PPF_CUDA_TRY(memcpy_sync(trans, r.trans, K * 12, cudaMemcpyDeviceToHost));
+    if (rots) PPF_CUDA_TRY(memcpy_sync(rots, r.rots, K * 16, cudaMemcpyDeviceToHost));
+    if (scores) PPF_CUDA_TRY(memcpy_sync(scores, r.scores, K * 4, cudaMemcpyDeviceToHost));
     if (pose) {
         // ppf.cu:80-93 -- only the winning pose crosses the bus (the reference copies all K)
         float t[3];
-        PPF_CUDA_TRY(cudaMemcpy(pose, r.transformations + (size_t)r.max_idx * 16, 64, cudaMemcpyDeviceToHost));
-        PPF_CUDA_TRY(cudaMemcpy(t, r.trans + r.max_idx, 12, cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(memcpy_sync(pose, r.transformations + (size_t)r.max_idx * 16, 64, cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(memcpy_sync(t, r.trans + r.max_idx, 12, cudaMemcpyDeviceToHost));
         pose[3] = t[0]; pose[7] = t[1]; pose[11] = t[2];
     }
     return PPF_OK;
@@ -354,7 +393,7 @@ int ppf_vote_histogram_shard(const ppf_model_t *m, const ppf_scene_t *s, unsigne
     int rc = vote_run(m->table, s->cloud, df, shard_rank, shard_count, 1, r, nullptr, nullptr);
     uint32_t h[4] = {0, 0, 0, 0};
     if (!rc && r.scalars) {
-        if (cudaMemcpy(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) rc = PPF_ERR_CUDA;
+        if (memcpy_sync(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) rc = PPF_ERR_CUDA;
     }
     if (!rc) {
         // ascending code order == the order thrust::sort + histogram() leaves (model.cu:148-151)
@@ -362,8 +401,8 @@ int ppf_vote_histogram_shard(const ppf_model_t *m, const ppf_scene_t *s, unsigne
         if (h[0] && codes_out && counts_out && h[0] <= capacity) {
             std::vector<unsigned long long> c(h[0]);
             std::vector<uint32_t> n(h[0]);
-            cudaMemcpy(c.data(), r.cand_codes, (size_t)h[0] * 8, cudaMemcpyDeviceToHost);
-            cudaMemcpy(n.data(), r.cand_counts, (size_t)h[0] * 4, cudaMemcpyDeviceToHost);
+            memcpy_sync(c.data(), r.cand_codes, (size_t)h[0] * 8, cudaMemcpyDeviceToHost);
+            memcpy_sync(n.data(), r.cand_counts, (size_t)h[0] * 4, cudaMemcpyDeviceToHost);
             std::vector<uint32_t> order(h[0]);
             for (uint32_t i = 0; i < h[0]; i++) order[i] = i;
             std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return c[a] < c[b]; });
@@ -459,8 +498,8 @@ extern "C" int ppf_lookup_cluster_cpu(const ppf_model_t *m, ppf_lookup_t *lk, fl
     if (!K) return PPF_OK;
     std::vector<float> T(K * 16);
     std::vector<uint32_t> cnt(K);
-    PPF_CUDA_TRY(cudaMemcpy(T.data(), lk->res.transformations, K * 64, cudaMemcpyDeviceToHost));
-    PPF_CUDA_TRY(cudaMemcpy(cnt.data(), lk->res.counts, K * 4, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(T.data(), lk->res.transformations, K * 64, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(cnt.data(), lk->res.counts, K * 4, cudaMemcpyDeviceToHost));
     std::vector<Pose> poses(K);
     for (size_t i = 0; i < K; i++) {
         for (int r = 0; r < 3; r++) { for (int c = 0; c < 3; c++) poses[i].R[r][c] = T[i * 16 + r * 4 + c]; poses[i].t[r] = T[i * 16 + r * 4 + 3]; }
@@ -471,12 +510,10 @@ extern "C" int ppf_lookup_cluster_cpu(const ppf_model_t *m, ppf_lookup_t *lk, fl
 }
 
 // ---- the drop-in boundary: ppf_registration (ppf.h:9-15, ppf.cu:29-106) -------------------
-extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes, const ppf_cloud_t *model_clouds,
-                                int num_models, const float *model_d_dists, unsigned ref_point_downsample_factor,
-                                float vote_count_threshold, int cpu_clustering, int use_l1_norm,
-                                int use_averaged_clusters, int device, const float *model_weights,
-                                float *poses_out, int *status_out) {
-    (void)model_weights;                                           // ignored by the reference too (ppf.cu:35)
+static int registration_run(const ppf_cloud_t *scene_clouds, int num_scenes, const ppf_cloud_t *model_clouds,
+                            int num_models, const float *model_d_dists, unsigned ref_point_downsample_factor,
+                            float vote_count_threshold, int cpu_clustering, int use_l1_norm,
+                            int use_averaged_clusters, int device, ppf_comm_t *comm, float *poses_out, int *status_out) {
     PPF_CHECK_ARG(scene_clouds && model_clouds && model_d_dists && poses_out && num_scenes >= 0 && num_models >= 0,
                   "registration: NULL argument");
     int ndev = 0;
@@ -484,7 +521,8 @@ extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes,
     if (ndev < 1) { set_last_error("registration: no CUDA device"); return PPF_ERR_CUDA; }
     int caller_device = 0;
     PPF_CUDA_TRY(cudaGetDevice(&caller_device));
-    PPF_CUDA_TRY(cudaSetDevice(std::min(ndev - 1, std::max(device, 0))));   // ppf.cu:45
+    // sharded: the rank's communicator lives on the device that is current; alone: the reference's rule (ppf.cu:45)
+    if (!comm) PPF_CUDA_TRY(cudaSetDevice(std::min(ndev - 1, std::max(device, 0))));
     struct RestoreDevice { int d; ~RestoreDevice() { cudaSetDevice(d); } } restore_device{caller_device};
     std::memset(poses_out, 0, (size_t)num_scenes * num_models * 64);
     // The reference rebuilds Scene and Model for every (scene, model) pair (ppf.cu:63-70). The model
@@ -511,7 +549,7 @@ extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes,
         rc = ppf_scene_create(c.xyz, c.xyz_stride, c.nrm, c.nrm_stride, c.n, PPF_MEM_HOST, &scene);
         for (int j = 0; j < num_models && !rc; j++) {
             float *pose = poses_out + ((size_t)i * num_models + j) * 16;
-            int st = lookup_run(models[j], scene, ref_point_downsample_factor, lk, !cpu_clustering);
+            int st = lookup_run(models[j], scene, ref_point_downsample_factor, lk, !cpu_clustering, comm_impl(comm));
             if (st == PPF_OK) {
                 if (cpu_clustering) st = ppf_lookup_cluster_cpu(models[j], lk, pose);      // ppf.cu:75-77
                 else st = ppf_lookup_get(lk, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, pose);
@@ -524,4 +562,28 @@ extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes,
     ppf_lookup_destroy(lk);
     for (auto *m : models) ppf_model_destroy(m);
     return rc;
+}
+
+extern "C" int ppf_registration(const ppf_cloud_t *scene_clouds, int num_scenes, const ppf_cloud_t *model_clouds,
+                                int num_models, const float *model_d_dists, unsigned ref_point_downsample_factor,
+                                float vote_count_threshold, int cpu_clustering, int use_l1_norm,
+                                int use_averaged_clusters, int device, const float *model_weights,
+                                float *poses_out, int *status_out) {
+    (void)model_weights;                                           // ignored by the reference too (ppf.cu:35)
+    return registration_run(scene_clouds, num_scenes, model_clouds, num_models, model_d_dists, ref_point_downsample_factor,
+                            vote_count_threshold, cpu_clustering, use_l1_norm, use_averaged_clusters, device, nullptr,
+                            poses_out, status_out);
+}
+
+// The same call made by every rank of `comm` with the same arguments (one process or host thread per GPU, the rank's
+// device current): the scene reference points are sharded over the ranks, every rank returns the same poses.
+extern "C" int ppf_registration_sharded(const ppf_cloud_t *scene_clouds, int num_scenes, const ppf_cloud_t *model_clouds,
+                                        int num_models, const float *model_d_dists,
+                                        unsigned ref_point_downsample_factor, float vote_count_threshold,
+                                        int cpu_clustering, int use_l1_norm, int use_averaged_clusters,
+                                        ppf_comm_t *comm, float *poses_out, int *status_out) {
+    PPF_CHECK_ARG(comm, "registration_sharded: comm is NULL");
+    return registration_run(scene_clouds, num_scenes, model_clouds, num_models, model_d_dists, ref_point_downsample_factor,
+                            vote_count_threshold, cpu_clustering, use_l1_norm, use_averaged_clusters, 0, comm,
+                            poses_out, status_out);
 }

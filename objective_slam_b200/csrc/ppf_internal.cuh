@@ -104,8 +104,21 @@ struct Workspace {
     void release();
 };
 
+// The exchanges between the ranks of a sharded recognition (ppf_comm.cu).  All buffers are device memory; the calls
+// are issued on cur_stream() and every rank must make the same sequence of calls.
+struct Comm {
+    int rank = 0, world = 1;
+    virtual ~Comm() {}
+    virtual int allreduce_max_u32(uint32_t *dev, size_t n) = 0;
+    virtual int allreduce_sum_f32(float *dev, size_t n) = 0;
+    virtual int allgather_u32(const uint32_t *dev_send, uint32_t *dev_recv, size_t n) = 0;        // n words per rank
+    // rank r contributes bytes[r] bytes, which land at dev_recv + offsets[r] on every rank
+    virtual int allgatherv(const void *dev_send, void *dev_recv, const size_t *offsets, const size_t *bytes) = 0;
+};
+
 struct VoteResult {                           // device buffers of one ppf_lookup
-    Workspace ws;
+    Workspace ws, ws2;                        // ws: filter / clustering scratch; ws2: merge + ordering scratch
+    uint32_t cand_n = 0, local_max = 0;       // host copies of scalars[0], scalars[1] after the vote kernel
     // candidates emitted by the vote kernel (superset of the survivors)
     unsigned long long *cand_codes = nullptr;
     uint32_t *cand_counts = nullptr;
@@ -145,6 +158,11 @@ template <typename T> inline cudaError_t pooled_malloc(T **p, size_t bytes) { re
 // size of the scenes the next models will be matched against (0 = unknown): see ppf_set_expected_scene_points
 extern std::atomic<int> g_expected_scene_points;
 
+}  // namespace ppf
+struct ppf_comm;
+ppf::Comm *comm_impl(ppf_comm *c);            // ppf_comm.cu
+namespace ppf {
+
 // error plumbing (never exit(): SURVEY 8b "Errors")
 void set_last_error(const std::string &msg);
 #define PPF_CUDA_TRY(expr)                                                                 \
@@ -155,6 +173,12 @@ void set_last_error(const std::string &msg);
             return PPF_ERR_CUDA;                                                           \
         }                                                                                  \
     } while (0)
+
+// The library works on its own NON-BLOCKING stream: one per (host thread, device), created on first use.  Every
+// launch, async copy and CUB call of the calling thread goes to cur_stream(); an API call that hands results to the
+// host synchronises it (memcpy_sync).  Nothing touches the legacy default stream (SURVEY 8b "Threading").
+cudaStream_t cur_stream();
+cudaError_t memcpy_sync(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind);
 
 // every launch of one of OUR kernels is counted (bench.py reports it as gpu_launches)
 void count_launch(int n = 1);
@@ -174,6 +198,8 @@ int  model_table_get(const ModelTable &m, uint32_t *hashkeys, size_t *counts, si
 int  vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_rank, int shard_count,
               int emit_all, VoteResult &r, unsigned long long *pairs_out, int *launches);
 int  vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteResult &r);
+int  vote_finalize_dist(const ModelTable &m, Comm *comm, VoteResult &r, uint32_t *global_max_out);
+int  cluster_dist(const ModelTable &m, Comm *comm, VoteResult &r);
 int  order_survivors(VoteResult &r, size_t K, unsigned long long *codes_in, uint32_t *counts_in);
 size_t order_survivors_bytes(size_t K);
 int  vote_reserve_K(VoteResult &r, size_t K);

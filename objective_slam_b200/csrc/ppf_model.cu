@@ -229,8 +229,8 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
     const float *dx = xyz, *dn = nrm;
     if (mem == PPF_MEM_HOST) {
         float *tx = (float *)ws.take_bytes(bx), *tn = (float *)ws.take_bytes(bn);
-        PPF_CUDA_TRY(cudaMemcpyAsync(tx, xyz, bx, cudaMemcpyHostToDevice, 0));
-        PPF_CUDA_TRY(cudaMemcpyAsync(tn, nrm, bn, cudaMemcpyHostToDevice, 0));
+        PPF_CUDA_TRY(cudaMemcpyAsync(tx, xyz, bx, cudaMemcpyHostToDevice, cur_stream()));
+        PPF_CUDA_TRY(cudaMemcpyAsync(tn, nrm, bn, cudaMemcpyHostToDevice, cur_stream()));
         dx = tx; dn = tn;
     }
     const int grid = std::min((n + 255) / 256, 148 * 8);
@@ -242,35 +242,35 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
         void *tmp = ws.take_bytes(sort_tmp);
         c.order = ws.take<uint32_t>(n); c.inv = ws.take<uint32_t>(n);
         const float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
-        PPF_CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, 0));
-        bbox_kernel<<<grid, 256>>>(dx, xs, n, mm);
+        PPF_CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, cur_stream()));
+        bbox_kernel<<<grid, 256, 0, cur_stream()>>>(dx, xs, n, mm);
         count_launch();
-        morton_kernel<<<grid, 256>>>(dx, xs, n, mm, key, idx);
+        morton_kernel<<<grid, 256, 0, cur_stream()>>>(dx, xs, n, mm, key, idx);
         count_launch();
-        PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, key, key_s, idx, c.order, n, 0, 30));
-        invert_kernel<<<grid, 256>>>(c.order, n, c.inv);
+        PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, key, key_s, idx, c.order, n, 0, 30, cur_stream()));
+        invert_kernel<<<grid, 256, 0, cur_stream()>>>(c.order, n, c.inv);
         count_launch();
     }
-    pack_cloud_kernel<<<(n + 255) / 256, 256>>>(dx, xs, dn, ns, n, c.order, c.pos, c.nrm, c.fy, c.fz);
+    pack_cloud_kernel<<<(n + 255) / 256, 256, 0, cur_stream()>>>(dx, xs, dn, ns, n, c.order, c.pos, c.nrm, c.fy, c.fz);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     if (spatial_sort) {
         c.gbox_lo = ws.take<float4>(ng); c.gbox_hi = ws.take<float4>(ng);
         c.tbox_lo = ws.take<float4>(nt); c.tbox_hi = ws.take<float4>(nt);
         if (!c.gbox_lo || !c.gbox_hi || !c.tbox_lo || !c.tbox_hi) { set_last_error("cloud: block too small"); return PPF_ERR_CUDA; }
-        boxes_kernel<<<std::min((ng + 127) / 128, 148 * 8), 128>>>(c.pos, n, 32, c.gbox_lo, c.gbox_hi, ng);
+        boxes_kernel<<<std::min((ng + 127) / 128, 148 * 8), 128, 0, cur_stream()>>>(c.pos, n, 32, c.gbox_lo, c.gbox_hi, ng);
         count_launch();
-        boxes_kernel<<<std::min((nt + 127) / 128, 148 * 8), 128>>>(c.pos, n, kHitQueue, c.tbox_lo, c.tbox_hi, nt);
+        boxes_kernel<<<std::min((nt + 127) / 128, 148 * 8), 128, 0, cur_stream()>>>(c.pos, n, kHitQueue, c.tbox_lo, c.tbox_hi, nt);
         count_launch();
         PPF_CUDA_TRY(cudaGetLastError());
     }
     if (spatial_sort && mm_dev) {                       // host copy of the AABB: bounds the distance bins of the scene's pairs
         float mm_h[6];
-        PPF_CUDA_TRY(cudaMemcpyAsync(mm_h, mm_dev, sizeof(mm_h), cudaMemcpyDeviceToHost, 0));
-        PPF_CUDA_TRY(cudaStreamSynchronize(0));
+        PPF_CUDA_TRY(cudaMemcpyAsync(mm_h, mm_dev, sizeof(mm_h), cudaMemcpyDeviceToHost, cur_stream()));
+        PPF_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
         for (int k = 0; k < 3; k++) { c.bb_lo[k] = mm_h[k]; c.bb_hi[k] = mm_h[3 + k]; }
     }
-    PPF_CUDA_TRY(cudaStreamSynchronize(0));
+    PPF_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return PPF_OK;
 }
 
@@ -329,11 +329,11 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
     if (ppfs_host) PPF_CUDA_TRY(pooled_malloc(&dp, total * sizeof(float4)));
     if (keys_host) PPF_CUDA_TRY(pooled_malloc(&dk, total * sizeof(uint32_t)));
     int blocks = (int)std::min<size_t>((total + 255) / 256, 148 * 16);
-    features_tile_kernel<<<blocks, 256>>>(c.pos, c.nrm, c.inv, c.n, d_dist, 1.0f / d_dist, df, rb, re, ob, oe, dp, dk);
+    features_tile_kernel<<<blocks, 256, 0, cur_stream()>>>(c.pos, c.nrm, c.inv, c.n, d_dist, 1.0f / d_dist, df, rb, re, ob, oe, dp, dk);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
-    if (dp) PPF_CUDA_TRY(cudaMemcpy(ppfs_host, dp, total * sizeof(float4), cudaMemcpyDeviceToHost));
-    if (dk) PPF_CUDA_TRY(cudaMemcpy(keys_host, dk, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (dp) PPF_CUDA_TRY(memcpy_sync(ppfs_host, dp, total * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (dk) PPF_CUDA_TRY(memcpy_sync(keys_host, dk, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     pooled_free(dp); pooled_free(dk);
     return PPF_OK;
 }
@@ -492,17 +492,17 @@ int model_far_cells(const ModelTable &m, const Cloud &scene, const unsigned long
             unsigned long long *dc = nullptr; uint32_t *db = nullptr, *dn = nullptr;
             PPF_CUDA_TRY(pooled_malloc(&dc, (size_t)cap * 8)); PPF_CUDA_TRY(pooled_malloc(&db, (size_t)cap * 4));
             PPF_CUDA_TRY(pooled_malloc(&dn, 4));
-            PPF_CUDA_TRY(cudaMemsetAsync(dn, 0, 4, 0));
+            PPF_CUDA_TRY(cudaMemsetAsync(dn, 0, 4, cur_stream()));
             const unsigned long long total = (unsigned long long)(K_new - K_have) * kCellsPerDist;
-            far_cells_kernel<<<(int)std::min<unsigned long long>((total + 255) / 256, 148 * 32), 256>>>(
+            far_cells_kernel<<<(int)std::min<unsigned long long>((total + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(
                 m.hashkeys, m.U, K_have, K_new, m.d_dist, dc, db, cap, dn);
             count_launch();
             uint32_t cnt = 0;
-            cudaError_t e = cudaMemcpy(&cnt, dn, 4, cudaMemcpyDeviceToHost);
+            cudaError_t e = memcpy_sync(&cnt, dn, 4, cudaMemcpyDeviceToHost);
             std::vector<unsigned long long> hc(std::min(cnt, cap));
             std::vector<uint32_t> hb(hc.size());
-            if (e == cudaSuccess && !hc.empty()) e = cudaMemcpy(hc.data(), dc, hc.size() * 8, cudaMemcpyDeviceToHost);
-            if (e == cudaSuccess && !hc.empty()) e = cudaMemcpy(hb.data(), db, hb.size() * 4, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && !hc.empty()) e = memcpy_sync(hc.data(), dc, hc.size() * 8, cudaMemcpyDeviceToHost);
+            if (e == cudaSuccess && !hc.empty()) e = memcpy_sync(hb.data(), db, hb.size() * 4, cudaMemcpyDeviceToHost);
             pooled_free(dc); pooled_free(db); pooled_free(dn);
             PPF_CUDA_TRY(e);
             if (cnt > cap) { cap = cnt; continue; }                // rare: count, then fetch
@@ -518,8 +518,8 @@ int model_far_cells(const ModelTable &m, const Cloud &scene, const unsigned long
         if (!fc.cells_h.empty()) {
             PPF_CUDA_TRY(pooled_malloc(&fc.cells, fc.cells_h.size() * 8));
             PPF_CUDA_TRY(pooled_malloc(&fc.buckets, fc.buckets_h.size() * 4));
-            PPF_CUDA_TRY(cudaMemcpy(fc.cells, fc.cells_h.data(), fc.cells_h.size() * 8, cudaMemcpyHostToDevice));
-            PPF_CUDA_TRY(cudaMemcpy(fc.buckets, fc.buckets_h.data(), fc.buckets_h.size() * 4, cudaMemcpyHostToDevice));
+            PPF_CUDA_TRY(memcpy_sync(fc.cells, fc.cells_h.data(), fc.cells_h.size() * 8, cudaMemcpyHostToDevice));
+            PPF_CUDA_TRY(memcpy_sync(fc.buckets, fc.buckets_h.data(), fc.buckets_h.size() * 4, cudaMemcpyHostToDevice));
         }
     }
     // only the cells this scene can reach (the cache may cover a larger scene met earlier)
@@ -561,7 +561,7 @@ int model_build(ModelTable &m) {
     m.n_chunks = 1; m.chunk_rows = 32;
     if (!m.far) m.far = new FarCells();
     PPF_CUDA_TRY(pooled_malloc(&m.weights, std::max(1, n) * sizeof(float)));
-    if (n > 0) fill_kernel<<<(n + 255) / 256, 256>>>(m.weights, n, 1.0f);
+    if (n > 0) fill_kernel<<<(n + 255) / 256, 256, 0, cur_stream()>>>(m.weights, n, 1.0f);
     count_launch();
     // Every reference kernel returns early when count <= 1 (kernel.cu:406,461): a model with
     // fewer than two points has an all-zero key array, i.e. one bucket (key 0) that can never match.
@@ -574,10 +574,10 @@ int model_build(ModelTable &m) {
         PPF_CUDA_TRY(pooled_malloc(&m.entries, 4)); PPF_CUDA_TRY(pooled_malloc(&m.ranges, 8));
         PPF_CUDA_TRY(pooled_malloc(&m.cell2bucket, 4));
         uint32_t z = 0, one = 1;
-        cudaMemcpy(m.hashkeys, &z, 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(m.counts, &one, 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(m.first, &z, 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(m.map, &z, 4, cudaMemcpyHostToDevice);
+        memcpy_sync(m.hashkeys, &z, 4, cudaMemcpyHostToDevice);
+        memcpy_sync(m.counts, &one, 4, cudaMemcpyHostToDevice);
+        memcpy_sync(m.first, &z, 4, cudaMemcpyHostToDevice);
+        memcpy_sync(m.map, &z, 4, cudaMemcpyHostToDevice);
         return PPF_OK;
     }
 
@@ -603,24 +603,24 @@ int model_build(ModelTable &m) {
         set_last_error("model: scratch arena too small");
         return PPF_ERR_CUDA;
     }
-    PPF_CUDA_TRY(cudaMemsetAsync(d_maxkd, 0xFF, 4, 0));
+    PPF_CUDA_TRY(cudaMemsetAsync(d_maxkd, 0xFF, 4, cur_stream()));
     int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-    model_pairs_kernel<<<grid, 256>>>(m.cloud.pos, m.cloud.nrm, n, m.d_dist, m.inv_d_dist, keys, iota, d_maxkd);
+    model_pairs_kernel<<<grid, 256, 0, cur_stream()>>>(m.cloud.pos, m.cloud.nrm, n, m.d_dist, m.inv_d_dist, keys, iota, d_maxkd);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
 
     // sort (key, pair index): LSD radix sort, stable, so every bucket ascends in pair index
     m.map = (uint32_t *)pool_alloc(total * 4, &m.map_cap);      // the two N^2 arrays come from the block cache
     if (!m.map) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, keys, keys_sorted, iota, m.map, total));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, keys, keys_sorted, iota, m.map, total, 0, 32, cur_stream()));
 
     // run-length encode -> unique keys + counts (histogram(), util.hpp:30-52); scan -> first index.
     // keys / iota are dead after the sort and are reused as the RLE outputs.
     uint32_t *uk = keys, *uc = iota;
-    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, rle_tmp, keys_sorted, uk, uc, d_U, total));
+    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, rle_tmp, keys_sorted, uk, uc, d_U, total, cur_stream()));
     int h_maxkd = -1;
-    PPF_CUDA_TRY(cudaMemcpy(&m.U, d_U, 4, cudaMemcpyDeviceToHost));
-    PPF_CUDA_TRY(cudaMemcpy(&h_maxkd, d_maxkd, 4, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(&m.U, d_U, 4, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(&h_maxkd, d_maxkd, 4, cudaMemcpyDeviceToHost));
     if (h_maxkd >= 65536) {
         set_last_error("model: d_dist is more than 65536x smaller than the model extent");
         return PPF_ERR_UNSUPPORTED;
@@ -629,9 +629,9 @@ int model_build(ModelTable &m) {
     PPF_CUDA_TRY(pooled_malloc(&m.hashkeys, (size_t)m.U * 4));
     PPF_CUDA_TRY(pooled_malloc(&m.counts, (size_t)m.U * 4));
     PPF_CUDA_TRY(pooled_malloc(&m.first, (size_t)m.U * 4));
-    PPF_CUDA_TRY(cudaMemcpyAsync(m.hashkeys, uk, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, 0));
-    PPF_CUDA_TRY(cudaMemcpyAsync(m.counts, uc, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, 0));
-    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, m.counts, m.first, m.U));
+    PPF_CUDA_TRY(cudaMemcpyAsync(m.hashkeys, uk, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, cur_stream()));
+    PPF_CUDA_TRY(cudaMemcpyAsync(m.counts, uc, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, cur_stream()));
+    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, m.counts, m.first, m.U, cur_stream()));
 
     // Accumulator chunk geometry = which vote kernel serves this table.  The grouped kernel (small chunks,
     // big hit queue: ppf_vote_grouped.cu) wins when voting dominates, i.e. when buckets are long (10k-point
@@ -659,13 +659,13 @@ int model_build(ModelTable &m) {
     // vote payload in bucket order, per-chunk bucket slices, cell table
     m.entries = (uint32_t *)pool_alloc(total * 4, &m.entries_cap);
     if (!m.entries) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
-    entries_kernel<<<grid, 256>>>(m.map, m.cloud.pos, m.cloud.fy, m.cloud.fz, total, n, m.chunk_rows, m.entries);
+    entries_kernel<<<grid, 256, 0, cur_stream()>>>(m.map, m.cloud.pos, m.cloud.fy, m.cloud.fz, total, n, m.chunk_rows, m.entries);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     PPF_CUDA_TRY(pooled_malloc(&m.ranges, (size_t)m.U * m.n_chunks * sizeof(uint2)));
     {
         size_t t = (size_t)m.U * m.n_chunks;
-        chunk_ranges_kernel<<<(int)std::min<size_t>((t + 255) / 256, 148 * 32), 256>>>(
+        chunk_ranges_kernel<<<(int)std::min<size_t>((t + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(
             m.map, m.first, m.counts, m.U, n, m.chunk_rows, m.n_chunks, m.ranges);
         count_launch();
     }
@@ -673,12 +673,12 @@ int model_build(ModelTable &m) {
     size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
     PPF_CUDA_TRY(pooled_malloc(&m.cell2bucket, ncell * 4));
     if (m.K_d > 0) {
-        cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256>>>(m.hashkeys, m.U, m.K_d,
+        cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(m.hashkeys, m.U, m.K_d,
                                                                                        m.d_dist, m.cell2bucket);
         count_launch();
     }
     PPF_CUDA_TRY(cudaGetLastError());
-    PPF_CUDA_TRY(cudaDeviceSynchronize());
+    PPF_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
     return PPF_OK;
 }
 
@@ -698,7 +698,7 @@ constexpr size_t kIoChunk = (size_t)32 << 20;
 int dev_to_file(FILE *f, const void *dev, size_t bytes, std::vector<char> &buf) {
     for (size_t off = 0; off < bytes; off += kIoChunk) {
         const size_t n = std::min(kIoChunk, bytes - off);
-        PPF_CUDA_TRY(cudaMemcpy(buf.data(), (const char *)dev + off, n, cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(memcpy_sync(buf.data(), (const char *)dev + off, n, cudaMemcpyDeviceToHost));
         if (fwrite(buf.data(), 1, n, f) != n) { set_last_error("model save: short write"); return PPF_ERR_INVALID; }
     }
     return PPF_OK;
@@ -708,7 +708,7 @@ int file_to_dev(FILE *f, void **dev, size_t bytes, std::vector<char> &buf) {
     for (size_t off = 0; off < bytes; off += kIoChunk) {
         const size_t n = std::min(kIoChunk, bytes - off);
         if (fread(buf.data(), 1, n, f) != n) { set_last_error("model load: file truncated"); return PPF_ERR_INVALID; }
-        PPF_CUDA_TRY(cudaMemcpy((char *)*dev + off, buf.data(), n, cudaMemcpyHostToDevice));
+        PPF_CUDA_TRY(memcpy_sync((char *)*dev + off, buf.data(), n, cudaMemcpyHostToDevice));
     }
     return PPF_OK;
 }
@@ -795,11 +795,11 @@ static int model_validate(const ModelTable &m) {
     const size_t total = (size_t)m.cloud.n * m.cloud.n, ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
     uint32_t *flag = nullptr, h = 0;
     PPF_CUDA_TRY(pooled_malloc(&flag, 4));
-    cudaMemsetAsync(flag, 0, 4, 0);
-    validate_table_kernel<<<148 * 8, 256>>>(m.counts, m.first, m.hashkeys, m.map, m.entries, m.ranges, m.cell2bucket, m.U,
+    cudaMemsetAsync(flag, 0, 4, cur_stream());
+    validate_table_kernel<<<148 * 8, 256, 0, cur_stream()>>>(m.counts, m.first, m.hashkeys, m.map, m.entries, m.ranges, m.cell2bucket, m.U,
                                             total, m.cloud.n, m.n_chunks, m.chunk_rows, ncell, flag);
     count_launch();
-    cudaError_t e = cudaMemcpy(&h, flag, 4, cudaMemcpyDeviceToHost);
+    cudaError_t e = memcpy_sync(&h, flag, 4, cudaMemcpyDeviceToHost);
     pooled_free(flag);
     PPF_CUDA_TRY(e);
     if (h) {
@@ -841,11 +841,11 @@ int model_load(ModelTable &m, const char *path) {
 int model_table_get(const ModelTable &m, uint32_t *hashkeys, size_t *counts, size_t *first, size_t *map) {
     size_t total = (size_t)m.cloud.n * m.cloud.n;
     std::vector<uint32_t> tmp;
-    if (hashkeys && m.U) PPF_CUDA_TRY(cudaMemcpy(hashkeys, m.hashkeys, (size_t)m.U * 4, cudaMemcpyDeviceToHost));
+    if (hashkeys && m.U) PPF_CUDA_TRY(memcpy_sync(hashkeys, m.hashkeys, (size_t)m.U * 4, cudaMemcpyDeviceToHost));
     auto widen = [&](const uint32_t *dev, size_t cnt, size_t *out) -> int {
         if (!out || !cnt) return PPF_OK;
         tmp.resize(cnt);
-        PPF_CUDA_TRY(cudaMemcpy(tmp.data(), dev, cnt * 4, cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(memcpy_sync(tmp.data(), dev, cnt * 4, cudaMemcpyDeviceToHost));
         for (size_t i = 0; i < cnt; i++) out[i] = tmp[i];
         return PPF_OK;
     };

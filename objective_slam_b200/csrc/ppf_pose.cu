@@ -279,10 +279,10 @@ struct DevBuf {
     ~DevBuf() { pooled_free(p); }
     int up(const void *h, size_t bytes) {
         if (pooled_malloc(&p, bytes ? bytes : 4) != cudaSuccess) return PPF_ERR_CUDA;
-        if (h && bytes && cudaMemcpy(p, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return PPF_ERR_CUDA;
+        if (h && bytes && memcpy_sync(p, h, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return PPF_ERR_CUDA;
         return PPF_OK;
     }
-    int down(void *h, size_t bytes) { return (h && bytes && cudaMemcpy(h, p, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) ? PPF_ERR_CUDA : PPF_OK; }
+    int down(void *h, size_t bytes) { return (h && bytes && memcpy_sync(h, p, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) ? PPF_ERR_CUDA : PPF_OK; }
 };
 
 int op_point_pair_feature(const float *p1, const float *n1, const float *p2, const float *n2, size_t n, float d_dist,
@@ -292,7 +292,7 @@ int op_point_pair_feature(const float *p1, const float *n1, const float *p2, con
     DevBuf a, b, c, d, r, q, k;
     if (a.up(p1, n * 12) || b.up(n1, n * 12) || c.up(p2, n * 12) || d.up(n2, n * 12) || r.up(nullptr, n * 16) ||
         q.up(nullptr, n * 16) || k.up(nullptr, n * 4)) { set_last_error("point_pair_feature: device allocation/copy failed"); return PPF_ERR_CUDA; }
-    pair_feature_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256>>>(
+    pair_feature_kernel<<<(int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, cur_stream()>>>(
         (const float *)a.p, (const float *)b.p, (const float *)c.p, (const float *)d.p, n, d_dist,
         raw_out ? (float4 *)r.p : nullptr, disc_out ? (float4 *)q.p : nullptr, keys_out ? (uint32_t *)k.p : nullptr);
     count_launch();
@@ -309,7 +309,7 @@ int op_trans_model_scene(const float *m_r, const float *n_r_m, const float *m_i,
     const float *src[6] = {m_r, n_r_m, m_i, s_r, n_r_s, s_i};
     for (int i = 0; i < 6; i++) if (in[i].up(src[i], n * 12)) { set_last_error("trans_model_scene: upload failed"); return PPF_ERR_CUDA; }
     if (tm.up(nullptr, n * 64) || ts.up(nullptr, n * 64) || al.up(nullptr, n * 4) || ai.up(nullptr, n * 4)) { set_last_error("trans_model_scene: allocation failed"); return PPF_ERR_CUDA; }
-    trans_model_scene_kernel<<<(int)std::min<size_t>((n + 127) / 128, 148 * 8), 128>>>(
+    trans_model_scene_kernel<<<(int)std::min<size_t>((n + 127) / 128, 148 * 8), 128, 0, cur_stream()>>>(
         (const float *)in[0].p, (const float *)in[1].p, (const float *)in[2].p, (const float *)in[3].p, (const float *)in[4].p,
         (const float *)in[5].p, n, T_m_g ? (float *)tm.p : nullptr, T_s_g ? (float *)ts.p : nullptr,
         alpha ? (float *)al.p : nullptr, alpha_idx ? (uint32_t *)ai.p : nullptr);
@@ -324,12 +324,12 @@ static int blocks_for(size_t count) { return (int)std::min<size_t>(std::max<size
 int poses_run(const ModelTable &m, const Cloud &scene, VoteResult &r) {
     const int K = (int)r.K;
     if (K == 0) return PPF_OK;
-    PPF_CUDA_TRY(cudaMemsetAsync(r.transformations, 0, (size_t)K * 64, 0));
-    PPF_CUDA_TRY(cudaMemsetAsync(r.weighted, 0, (size_t)K * 4, 0));
-    pose_kernel<<<blocks_for(K), 256>>>(r.codes, m.cloud.pos, m.cloud.nrm, scene.pos, scene.nrm, scene.inv, scene.n,
+    PPF_CUDA_TRY(cudaMemsetAsync(r.transformations, 0, (size_t)K * 64, cur_stream()));
+    PPF_CUDA_TRY(cudaMemsetAsync(r.weighted, 0, (size_t)K * 4, cur_stream()));
+    pose_kernel<<<blocks_for(K), 256, 0, cur_stream()>>>(r.codes, m.cloud.pos, m.cloud.nrm, scene.pos, scene.nrm, scene.inv, scene.n,
                                         r.transformations, K);
     count_launch();
-    weight_kernel<<<blocks_for(K), 256>>>(r.codes, r.counts, m.weights, r.weighted, K);
+    weight_kernel<<<blocks_for(K), 256, 0, cur_stream()>>>(r.codes, r.counts, m.weights, r.weighted, K);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     return PPF_OK;
@@ -341,12 +341,25 @@ int cluster_finish(VoteResult &r) {
     if (K <= 1) return PPF_OK;
     uint32_t *d_arg = nullptr;
     PPF_CUDA_TRY(pooled_malloc(&d_arg, 4));
-    argmax_kernel<<<1, 1024>>>(r.scores, K, d_arg);
+    argmax_kernel<<<1, 1024, 0, cur_stream()>>>(r.scores, K, d_arg);
     count_launch();
-    cudaError_t e = cudaMemcpy(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost);
+    cudaError_t e = memcpy_sync(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost);
     pooled_free(d_arg);
     PPF_CUDA_TRY(e);
     return PPF_OK;
+}
+
+// Clustering of the (merged) survivor list.  With several ranks Model::ClusterTransformations is sharded: it is
+// quadratic in dense cells (6 ms at K = 50k, 332 ms at K = 396k on one GPU), so every rank scores an interleaved
+// slice of the poses against all of them, the slices are summed (entries outside a slice are 0: exact) and every
+// rank picks the same winner.  use_averaged_clusters needs every pose's averaged translation: replicated then.
+int cluster_dist(const ModelTable &m, Comm *comm, VoteResult &r) {
+    const int world = comm ? comm->world : 1;
+    if (world == 1 || m.use_averaged_clusters) return cluster_run(m, r);
+    int rc = cluster_run(m, r, comm->rank, world);
+    if (rc) return rc;
+    if (r.K > 1 && (rc = comm->allreduce_sum_f32(r.scores, r.K))) return rc;
+    return cluster_finish(r);
 }
 
 // shard / n_shards: score only the poses idx = shard (mod n_shards); the other scores stay 0 and max_idx is not
@@ -355,11 +368,11 @@ int cluster_run(const ModelTable &m, VoteResult &r, int shard, int n_shards) {
     const int K = (int)r.K;
     r.max_idx = 0;
     if (K == 0) return PPF_OK;
-    PPF_CUDA_TRY(cudaMemsetAsync(r.trans, 0, (size_t)K * sizeof(float3), 0));
-    PPF_CUDA_TRY(cudaMemsetAsync(r.rots, 0, (size_t)K * sizeof(float4), 0));
-    PPF_CUDA_TRY(cudaMemsetAsync(r.scores, 0, (size_t)K * 4, 0));
+    PPF_CUDA_TRY(cudaMemsetAsync(r.trans, 0, (size_t)K * sizeof(float3), cur_stream()));
+    PPF_CUDA_TRY(cudaMemsetAsync(r.rots, 0, (size_t)K * sizeof(float4), cur_stream()));
+    PPF_CUDA_TRY(cudaMemsetAsync(r.scores, 0, (size_t)K * 4, cur_stream()));
     if (K <= 1) return PPF_OK;
-    transquat_kernel<<<blocks_for(K), 256>>>(r.transformations, r.trans, r.rots, K);
+    transquat_kernel<<<blocks_for(K), 256, 0, cur_stream()>>>(r.transformations, r.trans, r.rots, K);
     count_launch();
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
@@ -375,24 +388,24 @@ int cluster_run(const ModelTable &m, VoteResult &r, int shard, int n_shards) {
         set_last_error("cluster: workspace too small");
         return PPF_ERR_CUDA;
     }
-    cellhash_kernel<<<blocks_for(K), 256>>>(r.trans, cell, adj, K, m.d_dist);
+    cellhash_kernel<<<blocks_for(K), 256, 0, cur_stream()>>>(r.trans, cell, adj, K, m.d_dist);
     count_launch();
-    iota_u32_kernel<<<blocks_for(K), 256>>>(iota, K);
+    iota_u32_kernel<<<blocks_for(K), 256, 0, cur_stream()>>>(iota, K);
     count_launch();
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, cell, shash, iota, sidx, K));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, cell, shash, iota, sidx, K, 0, 32, cur_stream()));
     // rot_clustering_kernel updates translations in place while neighbours read them (a race in the
     // reference when use_averaged_clusters is set); we read a snapshot instead, which is deterministic.
-    PPF_CUDA_TRY(cudaMemcpyAsync(tin, r.trans, (size_t)K * sizeof(float3), cudaMemcpyDeviceToDevice, 0));
+    PPF_CUDA_TRY(cudaMemcpyAsync(tin, r.trans, (size_t)K * sizeof(float3), cudaMemcpyDeviceToDevice, cur_stream()));
     const size_t mine = ((size_t)K + n_shards - 1) / n_shards;
-    cluster_kernel<<<(int)std::min<size_t>((mine * 32 + 255) / 256, 148 * 64), 256>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
+    cluster_kernel<<<(int)std::min<size_t>((mine * 32 + 255) / 256, 148 * 64), 256, 0, cur_stream()>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
                                            m.d_dist, m.use_l1_norm, m.use_averaged_clusters, shard, n_shards);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     if (n_shards > 1) return PPF_OK;
-    argmax_kernel<<<1, 1024>>>(r.scores, K, d_arg);
+    argmax_kernel<<<1, 1024, 0, cur_stream()>>>(r.scores, K, d_arg);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
-    PPF_CUDA_TRY(cudaMemcpy(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(&r.max_idx, d_arg, 4, cudaMemcpyDeviceToHost));
     return PPF_OK;
 }
 

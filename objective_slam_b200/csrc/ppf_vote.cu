@@ -250,6 +250,36 @@ __global__ void filter_kernel(const unsigned long long *codes, const uint32_t *c
     }
 }
 
+// The same with the candidate count and the global maximum read from device memory (scalars[0], scalars[1]: the
+// maximum may just have been all-reduced in place) and the survivor count written to scalars[2]: no host round trip
+// between the vote kernel, the exchange of the maximum and the filter.
+__global__ void filter_dev_kernel(const unsigned long long *codes, const uint32_t *counts, uint32_t cap, float thr,
+                                  uint32_t *scalars, unsigned long long *ocodes, uint32_t *ocounts) {
+    const uint32_t n = min(scalars[0], cap);
+    const float min_votecount = thr * (float)scalars[1];                       // model.cu:164
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t c = counts[i];
+        if ((float)c > min_votecount) {
+            const uint32_t s = atomicAdd(&scalars[2], 1u);
+            ocodes[s] = codes[i];
+            ocounts[s] = c;
+        }
+    }
+}
+// survivor records travel between the ranks as 12-byte triples (code lo, code hi, count)
+__global__ void pack_survivors_kernel(const unsigned long long *codes, const uint32_t *counts, uint32_t n, uint32_t *rec) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned long long c = codes[i];
+        rec[3 * i] = (uint32_t)c; rec[3 * i + 1] = (uint32_t)(c >> 32); rec[3 * i + 2] = counts[i];
+    }
+}
+__global__ void unpack_survivors_kernel(const uint32_t *rec, uint32_t n, unsigned long long *codes, uint32_t *counts) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        codes[i] = (unsigned long long)rec[3 * i] | ((unsigned long long)rec[3 * i + 1] << 32);
+        counts[i] = rec[3 * i + 2];
+    }
+}
+
 int Workspace::reserve(size_t bytes) {
     bytes += 16 * 256;                                     // alignment slack for up to 16 slices
     used = 0;
@@ -281,7 +311,7 @@ void vote_result_free(VoteResult &r) {
     pooled_free(r.replay);
     pooled_free(r.codes); pooled_free(r.counts); pooled_free(r.transformations); pooled_free(r.weighted);
     pooled_free(r.trans); pooled_free(r.rots); pooled_free(r.scores);
-    r.ws.release();
+    r.ws.release(); r.ws2.release();
     r = VoteResult();
 }
 
@@ -326,8 +356,9 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
     // kernel choice: made with the chunk geometry at model build time (ppf_model.cu)
     const bool use_grouped = m.prefer_grouped && vote_grouped_supported(m, ns);
     for (int attempt = 0; attempt < 8; attempt++) {
-        PPF_CUDA_TRY(cudaMemsetAsync(r.scalars, 0, 4 * sizeof(uint32_t), 0));
-        PPF_CUDA_TRY(cudaMemsetAsync(r.votes_total, 0, 2 * sizeof(unsigned long long), 0));
+        PPF_CUDA_TRY(cudaMemsetAsync(r.scalars, 0, 4 * sizeof(uint32_t), cur_stream()));
+        PPF_CUDA_TRY(cudaMemsetAsync(r.votes_total, 0, 2 * sizeof(unsigned long long), cur_stream()));
+        r.cand_n = 0; r.local_max = 0;
         if (R == 0 || m.cloud.n <= 1 || m.K_d == 0) return PPF_OK;
         VoteArgs a;
         a.spos = scene.pos; a.snrm = scene.nrm; a.sfy = scene.fy; a.sfz = scene.fz; a.ns = ns;
@@ -365,7 +396,7 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
                 PPF_CUDA_TRY(pooled_malloc(&r.sched, sched_words * sizeof(uint32_t)));
                 r.sched_cap = sched_words;
             }
-            PPF_CUDA_TRY(cudaMemsetAsync(r.sched, 0, sched_words * sizeof(uint32_t), 0));
+            PPF_CUDA_TRY(cudaMemsetAsync(r.sched, 0, sched_words * sizeof(uint32_t), cur_stream()));
             a.sched = r.sched;
             const size_t words = vote_grouped_scratch_words(m);
             if (r.acc_scratch_cap < words) {
@@ -386,17 +417,18 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
             if (rc) return rc;
         } else if (smem > 113 * 1024) {
             PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            vote_kernel<1024><<<(unsigned)grid, 1024, smem>>>(a);
+            vote_kernel<1024><<<(unsigned)grid, 1024, smem, cur_stream()>>>(a);
             count_launch();
         } else {
             PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            vote_kernel<512><<<(unsigned)grid, 512, smem>>>(a);
+            vote_kernel<512><<<(unsigned)grid, 512, smem, cur_stream()>>>(a);
             count_launch();
         }
         PPF_CUDA_TRY(cudaGetLastError());
         if (launches) (*launches)++;
         uint32_t h[4];
-        PPF_CUDA_TRY(cudaMemcpy(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(memcpy_sync(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+        r.cand_n = h[0]; r.local_max = h[1];
         if (h[0] <= r.cand_cap) return PPF_OK;
         // candidate buffer too small: grow and vote again (results are deterministic)
         r.cand_cap = (size_t)h[0] + (h[0] >> 2) + 1024;
@@ -422,27 +454,86 @@ size_t order_survivors_bytes(size_t K) {
     return K * 12 + std::max(tb, tb2) + 1024;
 }
 
-// codes_in / counts_in may live in r.ws (taken before the call); the scratch comes from r.ws too.
+// codes_in / counts_in may live in r.ws; the scratch comes from r.ws2 (reserved here).
 int order_survivors(VoteResult &r, size_t K, unsigned long long *codes_in, uint32_t *counts_in) {
     if (K == 0) { r.K = 0; return PPF_OK; }
     int rc = vote_reserve_K(r, K);
     if (rc) return rc;
+    if ((rc = r.ws2.reserve(order_survivors_bytes(K)))) return rc;
     size_t tb = 0, tb2 = 0;
-    unsigned long long *c1 = r.ws.take<unsigned long long>(K);
-    uint32_t *n1 = r.ws.take<uint32_t>(K);
+    unsigned long long *c1 = r.ws2.take<unsigned long long>(K);
+    uint32_t *n1 = r.ws2.take<uint32_t>(K);
     cub::DeviceRadixSort::SortPairs(nullptr, tb, codes_in, c1, counts_in, n1, K);
     cub::DeviceRadixSort::SortPairsDescending(nullptr, tb2, n1, r.counts, c1, r.codes, K);
-    void *tmp = r.ws.take_bytes(std::max(tb, tb2));
+    void *tmp = r.ws2.take_bytes(std::max(tb, tb2));
     if (!c1 || !n1 || !tmp) { set_last_error("order_survivors: workspace too small"); return PPF_ERR_CUDA; }
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, codes_in, c1, counts_in, n1, K));
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tb2, n1, r.counts, c1, r.codes, K));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, tb, codes_in, c1, counts_in, n1, K, 0, 64, cur_stream()));
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairsDescending(tmp, tb2, n1, r.counts, c1, r.codes, K, 0, 32, cur_stream()));
     r.K = K;
     return PPF_OK;
 }
 
+// Threshold + ordering of one rank's candidates, or of all ranks' when `comm` couples several: all_reduce(MAX) of the
+// vote maximum, local filter against the GLOBAL threshold, all_gather of the survivor records, ordering of the
+// merged list (identical on every rank).  Every rank makes the same collective calls whatever it has to contribute.
+int vote_finalize_dist(const ModelTable &m, Comm *comm, VoteResult &r, uint32_t *global_max_out) {
+    const int world = comm ? comm->world : 1;
+    r.K = 0;
+    if (!r.scalars) { set_last_error("finalize: no vote has run on this lookup"); return PPF_ERR_INVALID; }
+    if (world > 1) { int rc = comm->allreduce_max_u32(r.scalars + 1, 1); if (rc) return rc; }
+    const uint32_t n = (uint32_t)std::min<size_t>(r.cand_n, r.cand_cap);
+    int rc = r.ws.reserve((size_t)n * 12 + 512 + (size_t)world * 8);
+    if (rc) return rc;
+    unsigned long long *fc = r.ws.take<unsigned long long>(std::max<uint32_t>(n, 1));
+    uint32_t *fn = r.ws.take<uint32_t>(std::max<uint32_t>(n, 1));
+    uint32_t *d_counts = r.ws.take<uint32_t>(world);
+    if (!fc || !fn || !d_counts) { set_last_error("finalize: workspace too small"); return PPF_ERR_CUDA; }
+    PPF_CUDA_TRY(cudaMemsetAsync(r.scalars + 2, 0, 4, cur_stream()));
+    if (n) {
+        filter_dev_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, cur_stream()>>>(
+            r.cand_codes, r.cand_counts, (uint32_t)r.cand_cap, m.vote_count_threshold, r.scalars, fc, fn);
+        count_launch();
+        PPF_CUDA_TRY(cudaGetLastError());
+    }
+    uint32_t h[4];
+    std::vector<uint32_t> counts(world, 0);
+    if (world > 1) {
+        rc = comm->allgather_u32(r.scalars + 2, d_counts, 1);
+        if (rc) return rc;
+        PPF_CUDA_TRY(cudaMemcpyAsync(counts.data(), d_counts, (size_t)world * 4, cudaMemcpyDeviceToHost, cur_stream()));
+    }
+    PPF_CUDA_TRY(memcpy_sync(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+    if (global_max_out) *global_max_out = h[1];
+    const size_t K_local = h[2];
+    if (world == 1) return (h[1] == 0 || K_local == 0) ? PPF_OK : order_survivors(r, K_local, fc, fn);
+    std::vector<size_t> off(world), bytes(world);
+    size_t K = 0;
+    for (int i = 0; i < world; i++) { off[i] = K * 12; bytes[i] = (size_t)counts[i] * 12; K += counts[i]; }
+    // merged list: packed records in ws2; the unpacked (codes, counts) go to ws, re-reserved once fc / fn are packed
+    if ((rc = r.ws2.reserve((K + K_local) * 12 + 1024))) return rc;
+    uint32_t *send = r.ws2.take<uint32_t>(std::max<size_t>(K_local, 1) * 3), *recv = r.ws2.take<uint32_t>(std::max<size_t>(K, 1) * 3);
+    if (!send || !recv) { set_last_error("finalize: merge workspace too small"); return PPF_ERR_CUDA; }
+    if (K_local) {
+        pack_survivors_kernel<<<(int)std::min<size_t>((K_local + 255) / 256, 148 * 8), 256, 0, cur_stream()>>>(fc, fn, (uint32_t)K_local, send);
+        count_launch();
+    }
+    if ((rc = comm->allgatherv(send, recv, off.data(), bytes.data()))) return rc;
+    if (K == 0) return PPF_OK;
+    PPF_CUDA_TRY(cudaStreamSynchronize(cur_stream()));            // the pack kernel reads fc / fn until here
+    if ((rc = r.ws.reserve(K * 12 + 512))) return rc;
+    unsigned long long *mc = r.ws.take<unsigned long long>(K);
+    uint32_t *mn = r.ws.take<uint32_t>(K);
+    if (!mc || !mn) { set_last_error("finalize: merge workspace too small"); return PPF_ERR_CUDA; }
+    unpack_survivors_kernel<<<(int)std::min<size_t>((K + 255) / 256, 148 * 8), 256, 0, cur_stream()>>>(recv, (uint32_t)K, mc, mn);
+    count_launch();
+    PPF_CUDA_TRY(cudaGetLastError());
+    PPF_CUDA_TRY(cudaStreamSynchronize(cur_stream()));            // order_survivors re-reserves ws2 (recv lives there)
+    return order_survivors(r, K, mc, mn);
+}
+
 int vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteResult &r) {
     uint32_t h[4];
-    PPF_CUDA_TRY(cudaMemcpy(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(h, r.scalars, sizeof(h), cudaMemcpyDeviceToHost));
     uint32_t n = h[0];
     r.K = 0;
     if (n == 0 || global_max == 0) return PPF_OK;
@@ -451,14 +542,14 @@ int vote_finalize(const ModelTable &m, uint32_t global_max, int emit_all, VoteRe
     unsigned long long *fc = r.ws.take<unsigned long long>(n);
     uint32_t *fn = r.ws.take<uint32_t>(n);
     uint32_t *d_on = r.ws.take<uint32_t>(1);
-    PPF_CUDA_TRY(cudaMemsetAsync(d_on, 0, 4, 0));
-    filter_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256>>>(r.cand_codes, r.cand_counts, n,
+    PPF_CUDA_TRY(cudaMemsetAsync(d_on, 0, 4, cur_stream()));
+    filter_kernel<<<std::min<uint32_t>((n + 255) / 256, 148 * 8), 256, 0, cur_stream()>>>(r.cand_codes, r.cand_counts, n,
                                                                          m.vote_count_threshold, global_max,
                                                                          emit_all, fc, fn, d_on);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     uint32_t K = 0;
-    PPF_CUDA_TRY(cudaMemcpy(&K, d_on, 4, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(&K, d_on, 4, cudaMemcpyDeviceToHost));
     return order_survivors(r, K, fc, fn);
 }
 

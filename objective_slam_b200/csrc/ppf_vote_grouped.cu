@@ -679,9 +679,9 @@ int vote_grouped_launch(VoteArgs a, int ref_count) {
     const size_t smem = vote_grouped_smem(a.chunk_rows);
     PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vote_kernel_grouped<kGThreads, false><<<(unsigned)grid, kGThreads, smem>>>(a);
+    vote_kernel_grouped<kGThreads, false><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
     // reference points whose hits did not fit the queue (none on sparse scenes: the kernel then exits at once)
-    vote_kernel_grouped<kGThreads, true><<<(unsigned)grid, kGThreads, smem>>>(a);
+    vote_kernel_grouped<kGThreads, true><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
     count_launch(2);
     return PPF_OK;
 }

@@ -107,8 +107,8 @@ int voxel_grid_run(const float *xyz, int xs, const float *nrm, int ns, int n, in
     const float *dx = xyz, *dn = nrm;
     if (mem == PPF_MEM_HOST) {
         float *tx = (float *)ws.take_bytes(bx), *tn = (float *)ws.take_bytes(bn);
-        PPF_CUDA_TRY(cudaMemcpyAsync(tx, xyz, bx, cudaMemcpyHostToDevice, 0));
-        PPF_CUDA_TRY(cudaMemcpyAsync(tn, nrm, bn, cudaMemcpyHostToDevice, 0));
+        PPF_CUDA_TRY(cudaMemcpyAsync(tx, xyz, bx, cudaMemcpyHostToDevice, cur_stream()));
+        PPF_CUDA_TRY(cudaMemcpyAsync(tn, nrm, bn, cudaMemcpyHostToDevice, cur_stream()));
         dx = tx; dn = tn;
     }
     float *mm = ws.take<float>(6);
@@ -122,33 +122,33 @@ int voxel_grid_run(const float *xyz, int xs, const float *nrm, int ns, int n, in
         return PPF_ERR_CUDA;
     }
     const float init[6] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-    PPF_CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, 0));
-    PPF_CUDA_TRY(cudaMemsetAsync(d_nh, 0, 4, 0));
+    PPF_CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, cur_stream()));
+    PPF_CUDA_TRY(cudaMemsetAsync(d_nh, 0, 4, cur_stream()));
     int grid = std::min((n + 255) / 256, 148 * 8);
-    vg_minmax_kernel<<<grid, 256>>>(dx, xs, n, mm);
+    vg_minmax_kernel<<<grid, 256, 0, cur_stream()>>>(dx, xs, n, mm);
     count_launch();
     float h[6];
-    PPF_CUDA_TRY(cudaMemcpy(h, mm, sizeof(h), cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(h, mm, sizeof(h), cudaMemcpyDeviceToHost));
     if (!(h[0] <= h[3])) return PPF_OK;                                 // no finite point
     const float inv_leaf = 1.0f / leaf;
     int3 min_b = make_int3((int)floorf(h[0] * inv_leaf), (int)floorf(h[1] * inv_leaf), (int)floorf(h[2] * inv_leaf));
     int3 max_b = make_int3((int)floorf(h[3] * inv_leaf), (int)floorf(h[4] * inv_leaf), (int)floorf(h[5] * inv_leaf));
     int3 div_b = make_int3(max_b.x - min_b.x + 1, max_b.y - min_b.y + 1, max_b.z - min_b.z + 1);
-    vg_cell_kernel<<<grid, 256>>>(dx, xs, n, inv_leaf, min_b, div_b, cell, idx);
+    vg_cell_kernel<<<grid, 256, 0, cur_stream()>>>(dx, xs, n, inv_leaf, min_b, div_b, cell, idx);
     count_launch();
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, cell, cell_s, idx, idx_s, n));
-    vg_heads_kernel<<<grid, 256>>>(cell_s, n, heads, d_nh);
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, cell, cell_s, idx, idx_s, n, 0, 64, cur_stream()));
+    vg_heads_kernel<<<grid, 256, 0, cur_stream()>>>(cell_s, n, heads, d_nh);
     count_launch();
     uint32_t nh = 0;
-    PPF_CUDA_TRY(cudaMemcpy(&nh, d_nh, 4, cudaMemcpyDeviceToHost));
+    PPF_CUDA_TRY(memcpy_sync(&nh, d_nh, 4, cudaMemcpyDeviceToHost));
     if (nh == 0) return PPF_OK;
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortKeys(tmp, sort2_tmp, heads, heads_s, (int)nh));   // ascending cell order
-    vg_centroid_kernel<<<std::min(((int)nh + 127) / 128, 148 * 8), 128>>>(dx, xs, dn, ns, cell_s, idx_s, heads_s, (int)nh, n, oxyz, onrm);
+    PPF_CUDA_TRY(cub::DeviceRadixSort::SortKeys(tmp, sort2_tmp, heads, heads_s, (int)nh, 0, 32, cur_stream()));   // ascending cell order
+    vg_centroid_kernel<<<std::min(((int)nh + 127) / 128, 148 * 8), 128, 0, cur_stream()>>>(dx, xs, dn, ns, cell_s, idx_s, heads_s, (int)nh, n, oxyz, onrm);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     cudaMemcpyKind kind = (mem == PPF_MEM_HOST) ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
-    if (out_xyz) PPF_CUDA_TRY(cudaMemcpy(out_xyz, oxyz, (size_t)nh * 12, kind));
-    if (out_nrm) PPF_CUDA_TRY(cudaMemcpy(out_nrm, onrm, (size_t)nh * 12, kind));
+    if (out_xyz) PPF_CUDA_TRY(memcpy_sync(out_xyz, oxyz, (size_t)nh * 12, kind));
+    if (out_nrm) PPF_CUDA_TRY(memcpy_sync(out_nrm, onrm, (size_t)nh * 12, kind));
     *n_out = (int)nh;
     return PPF_OK;
 }

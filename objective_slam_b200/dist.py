@@ -9,7 +9,9 @@ required by the reference's semantics (model.cu:160-170):
      not a truncated top-k), after which pose computation runs replicated;
   3. clustering of the merged list is sharded too (every rank scores an interleaved slice of the poses against
      all of them) and the score slices are summed with one all_reduce, after which every rank picks the winner.
-One process per GPU, torch.distributed over NCCL (gloo on CPU for the tests).
+One process per GPU.  The product path is inside the library (ppf_model_lookup_sharded, NCCL on the library's own
+stream); torch.distributed only ships the NCCL unique id.  `merge_survivors` / `lookup_sharded_torch` state the same
+protocol with torch collectives (gloo on CPU for the tests).
 """
 from __future__ import annotations
 
@@ -67,8 +69,65 @@ def merge_survivors(codes: torch.Tensor, counts: torch.Tensor, local_max: int, t
     return codes, counts, g
 
 
-def lookup_sharded(model, scene, lookup, rank: int, world: int, group=None, arrays: bool = False):
-    """Model::ppf_lookup over `world` GPUs; returns the same LookupResult on every rank."""
+class Comm:
+    """The ranks of a sharded recognition (include/ppf_b200.h, ppf_comm_*): NCCL between processes (one GPU each),
+    or host threads of one process on one GPU (`Comm.local`, the single-GPU test vehicle)."""
+
+    def __init__(self, handle):
+        self._h = handle
+
+    @classmethod
+    def from_torch(cls, group=None) -> "Comm":
+        """One library-owned NCCL communicator over the ranks of a torch.distributed group: rank 0 draws the NCCL
+        unique id and torch.distributed (any backend) ships its 128 bytes; the collectives of a lookup then run
+        inside the library on its own stream, not through torch."""
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = ctypes.create_string_buffer(128)
+        if rank == 0:
+            C.check(C.lib.ppf_comm_unique_id(buf))
+        box = [buf.raw]
+        dist.broadcast_object_list(box, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+        h = ctypes.c_void_p()
+        C.check(C.lib.ppf_comm_create_nccl(ctypes.create_string_buffer(box[0], 128), rank, world, ctypes.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def local(cls, world: int):
+        """`world` communicators for `world` host threads of this process (all on the current GPU)."""
+        arr = (ctypes.c_void_p * world)()
+        C.check(C.lib.ppf_comm_create_local(world, arr))
+        return [cls(ctypes.c_void_p(arr[i])) for i in range(world)]
+
+    @property
+    def rank(self) -> int:
+        return C.lib.ppf_comm_rank(self._h)
+
+    @property
+    def size(self) -> int:
+        return C.lib.ppf_comm_size(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            C.lib.ppf_comm_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
+def lookup_sharded(model, scene, lookup, comm: Comm, arrays: bool = False):
+    """Model::ppf_lookup over the ranks of `comm` (ppf_model_lookup_sharded): the same LookupResult on every rank,
+    bit-identical to the single-GPU lookup.  Everything -- voting of the rank's reference points, all_reduce(MAX),
+    survivor all_gather, ordering, poses, sharded clustering + all_reduce(SUM), argmax -- runs inside the library."""
+    rc = C.check(C.lib.ppf_model_lookup_sharded(model._h, scene._h, scene.ref_point_downsample_factor, comm._h, lookup._h),
+                 allow=(C.PPF_ERR_NO_VOTES,))
+    return lookup.result(rc, arrays)
+
+
+def lookup_sharded_torch(model, scene, lookup, rank: int, world: int, group=None, arrays: bool = False):
+    """The same exchange written out with torch.distributed collectives over the staged C entry points
+    (ppf_lookup_vote / finalize / set_survivors / cluster_shard): the readable statement of the protocol, kept as
+    a cross-check of the library path (and usable with any torch backend)."""
     df = scene.ref_point_downsample_factor
     C.check(C.lib.ppf_lookup_vote(model._h, scene._h, df, rank, world, lookup._h))
     lmax = ctypes.c_uint32()
@@ -89,9 +148,7 @@ def lookup_sharded(model, scene, lookup, rank: int, world: int, group=None, arra
         torch.cuda.synchronize()
         C.check(C.lib.ppf_lookup_set_survivors(lookup._h, codes.data_ptr(), counts.data_ptr(), codes.numel()))
     C.check(C.lib.ppf_lookup_poses(model._h, scene._h, lookup._h))
-    if world > 1 and not getattr(model, "use_averaged_clusters", True):
-        # 3. clustering of the merged list is quadratic in dense cells (332 ms at K = 396k on one GPU): every rank
-        # scores an interleaved slice, the slices are summed (entries outside a slice are 0, so the sum is exact)
+    if world > 1 and not model.use_averaged_clusters:
         C.check(C.lib.ppf_lookup_cluster_shard(model._h, lookup._h, rank, world))
         scores = torch.zeros(max(codes.numel(), 1), dtype=torch.float32, device=dev)
         C.check(C.lib.ppf_lookup_copy_scores(lookup._h, scores.data_ptr()))
