@@ -37,8 +37,19 @@ REFS_PER_GPU_DF = 8          # ref_point_df = 8 / n_gpus
 SEED = 0xD205 + 2
 
 
+def load_synth():
+    """objective_slam_b200/synth.py loaded as a standalone module: the reference arm must not import the package
+    (its __init__ dlopens the CUDA library), and the generator is pure numpy."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ppf_b200_synth", os.path.join(ROOT, "objective_slam_b200", "synth.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[spec.name] = mod       # dataclasses / typing look the module up by name
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def make_workload(n_model=N_MODEL, n_scene=N_SCENE):
-    from objective_slam_b200 import synth
+    synth = load_synth()
     mp, mn = synth.make_model(n_model, seed=SEED)
     sp, sn, T = synth.make_scene(mp, mn, n_scene, seed=SEED + 1)
     return mp, mn, sp, sn, synth.d_dist_for(mp, TAU_D), T
@@ -95,6 +106,22 @@ def measured_peaks():
         return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def measured_atoms_per_clk(grouped: bool):
+    """Shared-memory atomic increments per clock per SM, measured in THIS run on this GPU by
+    tools/microbench/libppf_peaks.so (conflict-free lanes for the grouped kernel, random cells for the classic one).
+    Falls back to the figures recorded in profiles/r02_smem_atomics.txt when the library is missing."""
+    fallback = (17.8, "conflict-free") if grouped else (12.15, "random cell")
+    try:
+        L = ctypes.CDLL(os.path.join(ROOT, "tools", "microbench", "libppf_peaks.so"))
+        L.peak_smem_atomics.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double)]
+        x = ctypes.c_double()
+        if L.peak_smem_atomics(1 if grouped else 0, ctypes.byref(x)) == 0 and x.value > 0:
+            return x.value, fallback[1], "measured in this run (tools/microbench/peaks.cu)"
+    except OSError:
+        pass
+    return fallback[0], fallback[1], "recorded (profiles/r02_smem_atomics.txt): libppf_peaks.so not built"
 
 
 def ncu_traffic_bytes_per_vote():
@@ -186,7 +213,16 @@ def run_reference(args, rank):
                                    "model table rebuilt per step but not timed"},
         "e2e": {"value": v, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "note": "CPU port of the reference's CUDA path (oracle/ppf_oracle.c, OpenMP): the reference itself is CUDA-only "
+                "(sm_35 flags, PCL/Eigen/Boost host code) and its MATLAB / PCL CPU pipelines cannot run here; each step "
+                "is a bounded SAMPLE of configs[1] (same per-pair and per-vote work, not the whole scene).  The strongest "
+                "CPU comparator measured is cpu_baseline_pcl_style; the reference's own kernels recompiled for sm_100a "
+                "are timed on the GPU in profiles/r01_reference_gpu.txt",
     }
+    try:
+        line["cpu_baseline_pcl_style"] = cpu_baseline_pcl_style(mp, mn, sp, sn, d, df)
+    except Exception as e:  # the comparator is informative only
+        line["cpu_baseline_pcl_style"] = {"error": str(e)}
     print(json.dumps(line), flush=True)
 
 
@@ -199,6 +235,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the configs[0]/[2]/[3]/[4] block of the N=1 line")
     ap.add_argument("--n-model", type=int, default=N_MODEL)
     ap.add_argument("--n-scene", type=int, default=N_SCENE)
     args = ap.parse_args()
@@ -222,7 +259,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import objective_slam_b200 as ppf
     from objective_slam_b200 import _capi as C
-    from objective_slam_b200.dist import lookup_sharded
+    from objective_slam_b200.dist import Comm, lookup_sharded
 
     df = max(1, REFS_PER_GPU_DF // world)
     mp, mn, sp, sn, d, T = make_workload(args.n_model, args.n_scene)
@@ -230,20 +267,37 @@ def main():
     sp_d, sn_d = torch.from_numpy(sp).to(dev), torch.from_numpy(sn).to(dev)
     model = ppf.Model(mp, mn, d)                       # prebuilt, replicated on every rank
     lk = ppf.Lookup()
+    # library-owned NCCL communicator (ppf_comm_create_nccl): the collectives of a sharded lookup run inside
+    # libppf_b200.so on its own stream; torch.distributed only ships the 128-byte NCCL id and the timing reductions
+    comm = Comm.from_torch() if world > 1 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def lookup(m, scene, lookup_obj):
+        if comm is not None:
+            return lookup_sharded(m, scene, lookup_obj, comm, arrays=False)
+        rc = C.check(C.lib.ppf_model_lookup(m._h, scene._h, scene.ref_point_downsample_factor, lookup_obj._h),
+                     allow=(C.PPF_ERR_NO_VOTES,))
+        return lookup_obj.result(rc, arrays=False)
+
     def step():
         scene = ppf.Scene(sp_d, sn_d, d, df)          # device-resident cloud -> frames
-        res = lookup_sharded(model, scene, lk, rank, world, arrays=False)
+        res = lookup(model, scene, lk)
         scene.close()
         return res
 
+    # ---- N > 1: the sharded lookup must give the unsharded answer (bit-equal survivors, scores, pose) before it is timed
+    parity_sharded = None
+    if world > 1:
+        parity_sharded = check_sharded_parity(ppf, C, comm, lookup_sharded)
+
     for _ in range(args.warmup):
         res = step()
+    grouped = model.layout()[2]
+    atoms_per_clk, atoms_kind, atoms_src = measured_atoms_per_clk(grouped) if rank == 0 else (None, None, None)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -260,14 +314,20 @@ def main():
     barrier()
     wall = time.perf_counter() - t0
     launches = C.lib.ppf_kernel_launch_count() - launches0
+    # the library works on its own stream and every lookup ends synchronised (host pose out), so the torch events
+    # bracket complete steps; ms_vote is the library's own CUDA-event time of the vote kernel on ITS stream
     step_ms = [a.elapsed_time(b) for a, b in ev]
     clocks = sampler.stop() if rank == 0 else None
 
     tot = torch.tensor([sum(step_ms), wall * 1e3, sum(vote_ms)], dtype=torch.float64, device=dev)
     cnt = torch.tensor([pairs_local, votes_local], dtype=torch.int64, device=dev)
+    per_rank = torch.zeros(world, 3, dtype=torch.float64, device=dev)
+    per_rank[rank] = torch.tensor([sum(vote_ms) / args.steps, sum(step_ms) / args.steps, votes_local / args.steps],
+                                  dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         dist.all_reduce(cnt, op=dist.ReduceOp.SUM)
+        dist.all_reduce(per_rank, op=dist.ReduceOp.SUM)
     dev_ms, wall_ms, kvote_ms = [float(x) for x in tot.tolist()]
     pairs, votes = [int(x) for x in cnt.tolist()]
     value = pairs / (dev_ms * 1e-3)
@@ -298,8 +358,9 @@ def main():
             barrier()
             t = time.perf_counter()
             a_d, b_d = hs[0].to(dev, non_blocking=True), hs[1].to(dev, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
             scene = ppf.Scene(a_d, b_d, d, df)
-            r2 = lookup_sharded(model, scene, lk, rank, world, arrays=False)
+            r2 = lookup(model, scene, lk)
             scene.close()
             barrier()
             if i >= 2:
@@ -310,21 +371,23 @@ def main():
         e2e = {"value": R * args.n_scene / (float(m.item()) * 1e-3), "unit": "pairs/s",
                "h2d_bytes_per_step": int(sp.nbytes + sn.nbytes), "d2h_bytes_per_step": 64 + 4,
                "ms_per_call": float(m.item()),
-               "call": "host scene cloud -> H2D (every rank) -> sharded ppf_lookup (prebuilt replicated model) -> host pose"}
+               "call": "host scene cloud -> H2D (every rank) -> ppf_model_lookup_sharded (prebuilt replicated model) -> host pose"}
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
-        # dominant kernel: vote_kernel.  Algorithmic bytes = 4 B bucket entry per vote (DESIGN.md "vote kernel").
+        hbm_peak, hbm_src = measured_peaks()
+        # dominant kernel: the vote kernel.  Its unit of work is one vote = one shared-memory atomic increment of a
+        # Hough cell ("shared-atomic peak to be measured"): the binding resource is the SM's L1TEX data
+        # pipe (ATOMS + the LDS/STS of the staged entries) and instruction issue, not HBM -- the table is L2-resident
+        # by construction (measured DRAM bytes in `traffic`).
         votes_per_launch = votes / max(args.steps * world, 1)
         launch_ms = kvote_ms / max(args.steps, 1)
-        achieved = votes_per_launch * 4 / (launch_ms * 1e-3) / 1e9
+        votes_per_s_kernel = votes_per_launch / (launch_ms * 1e-3)
         tpv = ncu_traffic_bytes_per_vote()
         err_t = float(np.linalg.norm(res.pose[:3, 3].astype(np.float64) - T[:3, 3]))
-        grouped = model.layout()[2]
         kernel_name = "ppf::vote_kernel_grouped" if grouped else "ppf::vote_kernel"
-        # ceiling of the accumulate step: ATOMS issue rate measured by the microbenchmark.  The grouped kernel's
-        # ATOMS are conflict-free by construction (1.11 wavefronts each), the classic kernel's hit random banks.
-        atoms_per_clk, atoms_kind = (17.8, "conflict-free") if grouped else (12.15, "random cell")
+        sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+        n_sm = torch.cuda.get_device_properties(dev).multi_processor_count
+        atoms_peak = atoms_per_clk * n_sm * sm_mhz * 1e6
         line = {
             "metric": "scene point-pairs voted/sec", "value": value, "unit": "pairs/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
@@ -341,30 +404,147 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "e2e": e2e,
-            "roofline": {"kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak,
-                         "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-                         "algorithmic_bytes_per_vote": 4, "votes_per_launch": votes_per_launch,
-                         "launch_ms": launch_ms,
+            "roofline": {"kernel": kernel_name, "bound": "smem-atomic (L1TEX data pipe)",
+                         "achieved": votes_per_s_kernel, "peak": atoms_peak, "unit": "votes/s",
+                         "frac": votes_per_s_kernel / atoms_peak,
+                         "peak_source": f"{atoms_per_clk:.2f} shared-memory atomic increments/clk/SM ({atoms_kind} lanes; "
+                                        f"{atoms_src}) x {n_sm} SMs x {sm_mhz:.0f} MHz SM clock under load",
+                         "votes_per_launch": votes_per_launch, "launch_ms": launch_ms,
                          "traffic": (tpv * votes_per_launch) if tpv is not None else None,
-                         "note": "algorithmic traffic = one 4-byte bucket entry per vote (SURVEY 8d); the kernel "
-                                 "fetches an entry once per group of hits and mostly from L2 (measured DRAM bytes in "
-                                 "`traffic`), so frac > 1 is expected: the binding limits are the shared-memory "
-                                 "atomic / L1TEX data pipe and instruction issue, reported in roofline_atomic"},
-            "roofline_atomic": {"bound": "smem-atomic issue", "achieved": votes_per_launch / (launch_ms * 1e-3),
-                                "peak": atoms_per_clk * 148 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None,
-                                "unit": "votes/s",
-                                "peak_source": f"tools/microbench/smem_atomics.cu: {atoms_per_clk} ATOMS/clk/SM "
-                                               f"({atoms_kind}) x 148 SMs x SM clock under load"},
+                         "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
+                                           "this kernel on this workload (profiles/vote_kernel_ncu_summary.json), per launch",
+                         "hbm": {"algorithmic_bytes_per_vote": 4,
+                                 "algorithmic_GBps": votes_per_s_kernel * 4 / 1e9, "peak_GBps": hbm_peak,
+                                 "peak_source": hbm_src,
+                                 "note": "one 4-byte bucket entry per vote would need this much HBM bandwidth if the table "
+                                         "came from HBM per vote; it does not (an entry is fetched once per group of hits, "
+                                         "mostly from L2), so HBM is not the bound and no HBM fraction is claimed"}},
         }
-        if line["roofline_atomic"]["peak"]:
-            line["roofline_atomic"]["frac"] = line["roofline_atomic"]["achieved"] / line["roofline_atomic"]["peak"]
+        if world > 1:
+            line["per_rank"] = {"ms_vote": [round(x, 3) for x in per_rank[:, 0].tolist()],
+                                "ms_step": [round(x, 3) for x in per_rank[:, 1].tolist()],
+                                "votes_per_step": [int(x) for x in per_rank[:, 2].tolist()]}
+            line["parity_sharded"] = parity_sharded
+        if world == 1 and not args.no_configs:
+            line["configs"] = other_configs(ppf, C, torch, args)
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(mp, mn, sp, sn, d, df)
             line["cpu_baseline_drost_m"] = cpu_baseline_drost_m(mp, mn, sp, sn, d, df)
             line["cpu_baseline_pcl_style"] = cpu_baseline_pcl_style(mp, mn, sp, sn, d, df)
         print(json.dumps(line), flush=True)
+    if comm is not None:
+        comm.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def check_sharded_parity(ppf, C, comm, lookup_sharded):
+    """A small recognition run unsharded on this rank and sharded over all ranks: survivors (codes, counts), poses,
+    clustering scores, winner and pose must be bit-equal.  Returns True / False (every rank computes the same)."""
+    synth = load_synth()
+    mp, mn = synth.make_model(700, seed=SEED + 11)
+    sp, sn, _ = synth.make_scene(mp, mn, 3000, seed=SEED + 12)
+    d = synth.d_dist_for(mp, TAU_D)
+    m = ppf.Model(mp, mn, d)
+    sc = ppf.Scene(sp, sn, d, 2)
+    one = m.ppf_lookup(sc, arrays=True)
+    lk = ppf.Lookup()
+    sh = lookup_sharded(m, sc, lk, comm, arrays=True)
+    ok = (one.num_top_votes == sh.num_top_votes and one.max_idx == sh.max_idx
+          and (one.votes == sh.votes).all() and (one.voteCounts == sh.voteCounts).all()
+          and (one.transformations.view(np.uint32) == sh.transformations.view(np.uint32)).all()
+          and (one.vote_counts_out.view(np.uint32) == sh.vote_counts_out.view(np.uint32)).all()
+          and (one.pose.view(np.uint32) == sh.pose.view(np.uint32)).all())
+    lk.close(); sc.close(); m.close()
+    return bool(ok)
+
+
+def other_configs(ppf, C, torch, args):
+    """Driver-visible numbers for the other BASELINE.json configs that fit one GPU (seconds each; configs[1] is the
+    timed workload above).  Device-timed with the library's own events (ms_vote) and host wall clock around
+    synchronised calls (p50 over the repeats)."""
+    synth = load_synth()
+    out = {}
+
+    def timed_lookups(model, scene, reps):
+        ms, r = [], None
+        for i in range(reps + 2):
+            torch.cuda.synchronize(); t = time.perf_counter()
+            r = model.ppf_lookup(scene, arrays=False)
+            torch.cuda.synchronize()
+            if i >= 2:
+                ms.append((time.perf_counter() - t) * 1e3)
+        return statistics.median(ms), r
+
+    # configs[0]: the reference's own CPU-runnable case -- 1k-point model, scene = model under a rigid transform + noise
+    mp, mn = synth.make_model(1000, seed=SEED + 21)
+    sp, sn, T = synth.make_scene(mp, mn, 1000, seed=SEED + 22)
+    d = synth.d_dist_for(mp, TAU_D)
+    m, s = ppf.Model(mp, mn, d), ppf.Scene(sp, sn, d, 1)
+    p50, r = timed_lookups(m, s, 20)
+    out["configs[0]"] = {"workload": "1k-point model, 1k-point scene, ref_point_df=1", "p50_ms": p50,
+                         "pairs_per_s": r.num_scene_pairs / (p50 * 1e-3), "votes_per_s": r.num_nonunique_votes / (p50 * 1e-3),
+                         "votes_per_pair": r.num_nonunique_votes / max(r.num_scene_pairs, 1), "ms_vote_kernel": r.ms_vote,
+                         "pose_translation_error": float(np.linalg.norm(r.pose[:3, 3] - T[:3, 3])),
+                         "grouped_kernel": m.layout()[2]}
+    s.close(); m.close()
+
+    # configs[2]: model hash build stress -- 5k-point model, 25M pairs (ppf_model_create, host cloud in)
+    mp, mn = synth.make_model(5000, seed=SEED + 3)
+    d = synth.d_dist_for(mp, TAU_D)
+    ts = []
+    for i in range(12):
+        torch.cuda.synchronize(); t = time.perf_counter()
+        m = ppf.Model(mp, mn, d)
+        torch.cuda.synchronize()
+        if i >= 2:
+            ts.append((time.perf_counter() - t) * 1e3)
+        m.close()
+    hbm, _ = measured_peaks()
+    p50 = statistics.median(ts)
+    out["configs[2]"] = {"workload": "5k-point model, 25M model pairs: ppf_model_create from a host cloud", "p50_ms": p50,
+                         "model_pairs_per_s": 25e6 / (p50 * 1e-3), "ceiling_model_pairs_per_s": hbm * 1e9 / 76,
+                         "frac_of_ceiling": 25e6 / (p50 * 1e-3) / (hbm * 1e9 / 76),
+                         "ceiling": "76 B per model pair (SURVEY 8d) at the measured HBM bandwidth"}
+
+    # configs[3] on one GPU: 20 models against one 200k-point scene through ppf_registration (host clouds in, poses out)
+    rng = np.random.default_rng(SEED + 30)
+    models = [synth.make_model(1500 + 100 * (i % 6), seed=SEED + 31 + i) for i in range(20)]
+    sp0, sn0, T3 = synth.make_scene(models[0][0], models[0][1], 20000, seed=SEED + 60)
+    lp, ln = synth.make_lattice_scene(180000, pitch=1.5)
+    sp3 = np.concatenate([sp0, lp + sp0.min(0)]).astype(np.float32); sn3 = np.concatenate([sn0, ln]).astype(np.float32)
+    perm = rng.permutation(len(sp3)); sp3, sn3 = sp3[perm], sn3[perm]
+    dd = [synth.d_dist_for(p, TAU_D) for p, _ in models]
+    ts = []
+    for i in range(1):                               # one call (tens of seconds): pools and clocks are warm from the steps above
+        torch.cuda.synchronize(); t = time.perf_counter()
+        poses, status = ppf.ppf_registration([(sp3, sn3)], models, dd, 8, 0.4)
+        torch.cuda.synchronize()
+        ts.append((time.perf_counter() - t) * 1e3)
+    R = (len(sp3) + 7) // 8
+    p50 = statistics.median(ts)
+    out["configs[3]"] = {"workload": "20 models (1.5k-2k points each) x one 200k-point scene (object 0 planted + room lattice), "
+                                     "ref_point_df=8, one ppf_registration call on ONE GPU (model builds inside)",
+                         "p50_ms_per_scene": p50, "pairs_per_s": 20 * R * len(sp3) / (p50 * 1e-3),
+                         "planted_model_translation_error": float(np.linalg.norm(poses[0, 0, :3, 3] - T3[:3, 3])),
+                         "status_ok": int((status == 0).sum())}
+
+    # configs[4]: dense KinFu-scale scene -- 1M points (room lattice + one object), 2k-point model
+    mp, mn = synth.make_model(2000, seed=0xD209)
+    sp0, sn0, T = synth.make_scene(mp, mn, 20000, seed=0xD20A)
+    lp, ln = synth.make_lattice_scene(1000000 - 20000, pitch=1.0)
+    sp = np.concatenate([sp0, lp + sp0.min(0)]).astype(np.float32); sn = np.concatenate([sn0, ln]).astype(np.float32)
+    perm = np.random.default_rng(1).permutation(len(sp)); sp, sn = sp[perm], sn[perm]
+    d = synth.d_dist_for(mp, TAU_D)
+    m, s = ppf.Model(mp, mn, d, expected_scene_points=len(sp)), ppf.Scene(sp, sn, d, 8)
+    p50, r = timed_lookups(m, s, 3)
+    out["configs[4]"] = {"workload": "2k-point model, 1M-point scene (room lattice + one object), ref_point_df=8", "p50_ms": p50,
+                         "pairs_per_s": r.num_scene_pairs / (p50 * 1e-3), "votes_per_s": r.num_nonunique_votes / (p50 * 1e-3),
+                         "votes_per_pair": r.num_nonunique_votes / max(r.num_scene_pairs, 1), "ms_vote_kernel": r.ms_vote,
+                         "pose_translation_error": float(np.linalg.norm(r.pose[:3, 3] - T[:3, 3])),
+                         "grouped_kernel": m.layout()[2]}
+    s.close(); m.close()
+    return out
 
 
 if __name__ == "__main__":

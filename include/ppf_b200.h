@@ -71,6 +71,12 @@ void ppf_release_cached_memory(void);
  * points favour the grouped kernel even for small models); results never depend on it.  ppf_registration sets
  * it from its own scene list. */
 void ppf_set_expected_scene_points(int n);
+/* The library issues all its work on its own non-blocking CUDA stream, one per (host thread, device), never on the
+ * legacy default stream (the reference uses the default stream and cudaDeviceSynchronize throughout).  Device
+ * inputs must be complete before a call; results handed to the host are synchronised by the call.  This returns
+ * the calling thread's stream on the current device (a cudaStream_t) so that a host can record events on it or
+ * order its own work against it. */
+int ppf_current_stream(void **stream_out);
 
 /* ---- Scene ------------------------------------------------------------------ */
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n,

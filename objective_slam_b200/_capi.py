@@ -18,6 +18,7 @@ PPF_MEM_HOST, PPF_MEM_DEVICE = 0, 1
 # every symbol include/ppf_b200.h declares (tests check that the library exports them all)
 EXPORTS = [
     "ppf_last_error", "ppf_version", "ppf_kernel_launch_count", "ppf_release_cached_memory", "ppf_set_expected_scene_points",
+    "ppf_current_stream",
     "ppf_scene_create", "ppf_scene_destroy", "ppf_scene_num_points", "ppf_scene_features",
     "ppf_model_create", "ppf_model_destroy", "ppf_model_num_points", "ppf_model_save", "ppf_model_load",
     "ppf_model_layout", "ppf_model_params", "ppf_model_table_sizes",
@@ -77,6 +78,7 @@ def _load():
     L.ppf_release_cached_memory.restype = None
     L.ppf_set_expected_scene_points.argtypes = [ci]
     L.ppf_set_expected_scene_points.restype = None
+    L.ppf_current_stream.argtypes = [P(vp)]
     L.ppf_scene_create.argtypes = [vp, ci, vp, ci, ci, ci, P(vp)]
     L.ppf_scene_destroy.argtypes = [vp]
     L.ppf_scene_destroy.restype = None

@@ -73,6 +73,11 @@ const char *ppf_version(void) { return "ppf_b200 0.1 (sm_100a)"; }
 uint64_t ppf_kernel_launch_count(void) { return g_kernel_launches.load(); }
 void ppf_release_cached_memory(void) { pool_trim(); }
 void ppf_set_expected_scene_points(int n) { g_expected_scene_points.store(n > 0 ? n : 0); }
+int ppf_current_stream(void **stream_out) {
+    if (!stream_out) { set_last_error("current_stream: NULL argument"); return PPF_ERR_INVALID; }
+    *stream_out = (void *)cur_stream();
+    return PPF_OK;
+}
 
 // ---- Scene ------------------------------------------------------------------------
 int ppf_scene_create(const float *xyz, int xyz_stride, const float *nrm, int nrm_stride, int n, int mem,

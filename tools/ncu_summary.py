@@ -16,6 +16,8 @@ want_prefix = ("gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_wr
                "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum",
                "l1tex__data_pipe_lsu_wavefronts_mem_shared_op_st.sum",
                "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_atom.sum",
+               "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_ld.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared_op_st.sum",
+               "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
                "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
                "smsp__inst_executed.sum", "smsp__thread_inst_executed.sum", "smsp__inst_executed_op_shared_atom.sum",
                "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "launch__shared_mem_per_block_dynamic",
