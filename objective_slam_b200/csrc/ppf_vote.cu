@@ -342,6 +342,7 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
     }
     if (!r.cand_codes) {
         r.cand_cap = emit_all ? (size_t)1 << 24 : (size_t)1 << 22;
+        if (const char *e = getenv("PPF_B200_CAND_CAP")) r.cand_cap = (size_t)std::max(1, atoi(e));   // test hook: force the overflow path
         PPF_CUDA_TRY(pooled_malloc(&r.cand_codes, r.cand_cap * 8));
         PPF_CUDA_TRY(pooled_malloc(&r.cand_counts, r.cand_cap * 4));
     }
@@ -355,8 +356,14 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
     if (launches) *launches = 0;
     // kernel choice: made with the chunk geometry at model build time (ppf_model.cu)
     const bool use_grouped = m.prefer_grouped && vote_grouped_supported(m, ns);
-    for (int attempt = 0; attempt < 8; attempt++) {
+    // Candidate overflow (more cells above the running threshold than the buffer holds): the buffer grows to the
+    // number the first pass COUNTED and the second pass starts from the first pass's maximum, so that it emits
+    // exactly the cells above the final threshold -- never more than the first pass counted: two passes at most.
+    uint32_t seed_max = 0;
+    for (int attempt = 0; attempt < 3; attempt++) {
         PPF_CUDA_TRY(cudaMemsetAsync(r.scalars, 0, 4 * sizeof(uint32_t), cur_stream()));
+        if (seed_max && !emit_all)
+            PPF_CUDA_TRY(cudaMemcpyAsync(r.scalars + 1, &seed_max, sizeof(uint32_t), cudaMemcpyHostToDevice, cur_stream()));
         PPF_CUDA_TRY(cudaMemsetAsync(r.votes_total, 0, 2 * sizeof(unsigned long long), cur_stream()));
         r.cand_n = 0; r.local_max = 0;
         if (R == 0 || m.cloud.n <= 1 || m.K_d == 0) return PPF_OK;
@@ -431,7 +438,8 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         r.cand_n = h[0]; r.local_max = h[1];
         if (h[0] <= r.cand_cap) return PPF_OK;
         // candidate buffer too small: grow and vote again (results are deterministic)
-        r.cand_cap = (size_t)h[0] + (h[0] >> 2) + 1024;
+        seed_max = h[1];
+        r.cand_cap = (size_t)h[0] + 1024;
         pooled_free(r.cand_codes); pooled_free(r.cand_counts);
         r.cand_codes = nullptr; r.cand_counts = nullptr;
         PPF_CUDA_TRY(pooled_malloc(&r.cand_codes, r.cand_cap * 8));

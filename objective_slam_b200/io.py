@@ -5,6 +5,8 @@ reference's validation metric.  Plain numpy; nothing here is on the hot path.
   float/double (or integer) scalar properties, among them `x y z` and either `nx ny nz` (what
   matlab/write_ply_cloud.m:37-53 writes through ply_write.m) or `normal_x normal_y normal_z` (PCL's names,
   alignment.cpp:212,241 reads them with pcl::io::loadPLYFile<PointNormal>).  Other elements (faces) are skipped.
+* `.trans_adj` side files (compute_trans_adj.m:2-16, compute_normals.m:11-22): the per-dataset shift into the positive
+  octant that the reference's pipeline applies before recognition, and the pose bookkeeping that goes with it.
 * Poses: 4x4 row-major text matrices, the format alignment.cpp:304-307 reads through util.hpp:95-104.
 * ht_dist / validation: linalg.cu:9-20 and alignment.cpp:317-323.
 """
@@ -104,6 +106,63 @@ def write_ply(path, points, normals=None, fmt="ascii", pcl_names=False):
             f.write(data.astype(">f4").tobytes())
         else:
             raise ValueError(fmt)
+
+
+def write_ply_matlab(path, points, normals):
+    """Byte layout of matlab/utils/ply/ply_write.m in 'ascii' mode for the struct write_ply_cloud.m:37-53 and
+    compute_normals.m:6-15 build: its comment line, `property float` x y z nx ny nz (doubles are narrowed to float
+    unless 'double' is asked for, ply_write.m:192-194), every value printed with '%-.6f ' (ply_write.m:89,225), i.e.
+    six decimals and a trailing blank before the newline."""
+    p = np.asarray(points, np.float64)
+    n = np.asarray(normals, np.float64)
+    with open(path, "w", newline="\n") as f:
+        f.write("ply\nformat ascii 1.0\ncomment created by MATLAB ply_write\n")
+        f.write(f"element vertex {len(p)}\n")
+        for name in ("x", "y", "z", "nx", "ny", "nz"):
+            f.write(f"property float {name}\n")
+        f.write("end_header\n")
+        for a, b in zip(p, n):
+            f.write("".join("%-.6f " % v for v in (*a, *b)) + "\n")
+
+
+# ---- .trans_adj: the shift that moves every cloud of a dataset into the positive octant ---------------------
+def compute_trans_adj(clouds):
+    """compute_trans_adj.m:2-16 over a list of point arrays: per axis max over the clouds of |min| + 1."""
+    t = np.zeros(3)
+    for pts in clouds:
+        t = np.maximum(t, np.abs(np.asarray(pts, np.float64).min(axis=0)) + 1.0)
+    return t
+
+
+def write_trans_adj(ply_path, trans_adj):
+    """compute_normals.m:17-22: `<output>.trans_adj`, one line '%f %f %f'."""
+    with open(str(ply_path) + ".trans_adj", "w", newline="\n") as f:
+        f.write("%f %f %f\n" % tuple(float(v) for v in np.asarray(trans_adj).reshape(3)))
+
+
+def read_trans_adj(ply_path):
+    """The shift stored next to a cloud by compute_normals.m, or None when the cloud has none."""
+    import os
+    path = str(ply_path) + ".trans_adj"
+    if not os.path.exists(path):
+        return None
+    v = np.loadtxt(path, dtype=np.float64).reshape(-1)
+    if v.size != 3:
+        raise ValueError(f"{path}: expected 3 numbers, got {v.size}")
+    return v
+
+
+def apply_trans_adj(points, trans_adj):
+    """compute_normals.m:11-13: points + trans_adj (the reference's pipeline wants positive coordinates)."""
+    return (np.asarray(points, np.float64) + np.asarray(trans_adj, np.float64).reshape(1, 3)).astype(np.float32)
+
+
+def pose_in_adjusted_frame(T, trans_adj_model, trans_adj_scene):
+    """A model->scene pose expressed between the ORIGINAL clouds, rewritten for clouds shifted by their .trans_adj:
+    x' = x + a_m, y' = y + a_s  =>  T' = Trans(a_s) T Trans(-a_m)."""
+    A = np.eye(4); A[:3, 3] = np.asarray(trans_adj_scene, np.float64).reshape(3)
+    B = np.eye(4); B[:3, 3] = -np.asarray(trans_adj_model, np.float64).reshape(3)
+    return A @ np.asarray(T, np.float64).reshape(4, 4) @ B
 
 
 def read_pose(path):

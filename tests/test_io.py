@@ -48,3 +48,32 @@ def test_voxel_grid_numpy_restatement_properties():
     assert len({tuple(c) for c in cells}) == len(q)                   # one point per leaf, centroid inside its leaf
     assert (np.linalg.norm(m, axis=1) <= 1.0 + 1e-5).all()            # averaged normals are not re-normalised
     assert np.linalg.norm(m, axis=1).min() < 0.999
+
+
+def test_matlab_ply_write_fixture_and_trans_adj(tmp_path):
+    """The layout matlab/utils/ply/ply_write.m emits for write_ply_cloud.m / compute_normals.m (committed fixture,
+    tests/golden/make_ply_fixture.py) is read back to 6 decimals, our writer reproduces it byte for byte, and the
+    .trans_adj side file round-trips (compute_normals.m:17-22)."""
+    import os
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    fix = os.path.join(here, "matlab_ply_write.ply")
+    vals = np.load(os.path.join(here, "matlab_ply_write_values.npy"))
+    p, n = io.read_ply(fix)
+    assert p.shape == (12, 3) and np.abs(p - vals[:, :3]).max() < 1e-5 and np.abs(n - vals[:, 3:]).max() < 1e-6
+    out = tmp_path / "again.ply"
+    io.write_ply_matlab(out, vals[:, :3], vals[:, 3:])
+    assert out.read_bytes() == open(fix, "rb").read()
+    adj = io.read_trans_adj(fix)
+    assert adj is not None and (p.min(0) > 0.99).all()                       # positive octant, min = 1 per axis
+    assert np.allclose(adj, io.compute_trans_adj([vals[:, :3] - adj]), atol=1e-5)
+    io.write_trans_adj(out, adj)
+    assert open(str(out) + ".trans_adj").read() == open(fix + ".trans_adj").read()
+    assert io.read_trans_adj(tmp_path / "missing.ply") is None
+    # a pose between the original clouds, rewritten for the shifted ones, maps shifted model points onto shifted scene points
+    mp, mn = synth.make_model(50, seed=1)
+    sp, sn, T = synth.make_scene(mp, mn, 50, seed=2, noise=0.0, normal_noise_deg=0.0)
+    a_m, a_s = np.array([3.0, 4.0, 5.0]), np.array([7.0, 1.0, 2.0])
+    T2 = io.pose_in_adjusted_frame(T, a_m, a_s)
+    x = io.apply_trans_adj(mp[:5], a_m).astype(np.float64)
+    y = (T[:3, :3] @ mp[:5].astype(np.float64).T).T + T[:3, 3] + a_s
+    assert np.abs((T2[:3, :3] @ x.T).T + T2[:3, 3] - y).max() < 1e-3

@@ -104,6 +104,14 @@ def test_hit_queue_overflow(monkeypatch):
     compare_all(mp, mn, sp, sn, d, 40)
 
 
+def test_candidate_buffer_overflow(monkeypatch):
+    """More cells above the running threshold than the candidate buffer holds (forced down to 64): the buffer grows
+    to the counted size and ONE more pass, seeded with the first pass's maximum, emits exactly the survivors."""
+    monkeypatch.setenv("PPF_B200_CAND_CAP", "64")
+    mp, mn, sp, sn, d, _ = clouds(300, 500, 0.05, seed=77)
+    compare_all(mp, mn, sp, sn, d, 1, thr=0.1)
+
+
 @pytest.mark.parametrize("l1,avg,thr", [(True, False, 0.4), (False, True, 0.4), (False, False, 0.9), (False, False, 0.0)])
 def test_lookup_options(l1, avg, thr):
     mp, mn, sp, sn, d, _ = clouds(250, 400, 0.06, seed=21)
@@ -160,6 +168,54 @@ def test_registration_boundary():
                 assert status[i, j] == 0 and (bits(r["pose"]) == bits(poses[i, j])).all()
             else:
                 assert not poses[i, j].any()
+
+
+@pytest.mark.parametrize("mem", ["host", "device"])
+def test_pointnormal_strided_clouds(mem):
+    """The layout INTEGRATION.md tells the maintainer to pass: pcl::PointNormal records of 12 floats
+    (x y z pad | normal_x normal_y normal_z pad | curvature pad pad pad), xyz_stride = nrm_stride = 12, the normal
+    pointer 4 floats into the record -- through the C ABI (ppf_scene_create / ppf_model_create / ppf_registration),
+    host and device memory.  Same bits as the packed N x 3 arrays; the padding holds NaNs that must never be read."""
+    import ctypes
+    import torch
+    import objective_slam_b200 as ppf
+    from objective_slam_b200 import _capi as C
+    mp, mn, sp, sn, d, _ = clouds(230, 410, 0.05, seed=91)
+
+    def records(p, n):
+        r = np.full((len(p), 12), np.nan, np.float32)
+        r[:, 0:3] = p; r[:, 4:7] = n
+        return r
+
+    want = ppf.Model(mp, mn, d).ppf_lookup(ppf.Scene(sp, sn, d, 2))
+    rm, rs = records(mp, mn), records(sp, sn)
+    if mem == "device":
+        tm, ts = torch.from_numpy(rm).cuda(), torch.from_numpy(rs).cuda()
+        torch.cuda.synchronize()
+        pm, ps, kind = tm.data_ptr(), ts.data_ptr(), C.PPF_MEM_DEVICE
+    else:
+        pm, ps, kind = rm.ctypes.data, rs.ctypes.data, C.PPF_MEM_HOST
+    hm, hs, lk = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+    C.check(C.lib.ppf_model_create(pm, 12, pm + 16, 12, len(mp), kind, float(d), 0.4, 0, 0, ctypes.byref(hm)))
+    C.check(C.lib.ppf_scene_create(ps, 12, ps + 16, 12, len(sp), kind, ctypes.byref(hs)))
+    C.check(C.lib.ppf_lookup_create(ctypes.byref(lk)))
+    C.check(C.lib.ppf_model_lookup(hm, hs, 2, lk))
+    pose = np.zeros((4, 4), np.float32)
+    C.check(C.lib.ppf_lookup_get(lk, None, None, None, None, None, None, None, pose.ctypes.data))
+    st = C.LookupStats()
+    C.check(C.lib.ppf_lookup_get_stats(lk, ctypes.byref(st)))
+    assert st.num_nonunique_votes == want.num_nonunique_votes and st.num_top_votes == want.num_top_votes
+    assert (bits(pose) == bits(want.pose)).all()
+    C.lib.ppf_lookup_destroy(lk); C.lib.ppf_scene_destroy(hs); C.lib.ppf_model_destroy(hm)
+    if mem == "host":       # the drop-in call with ppf_cloud_t descriptors of PointNormal records (host clouds only)
+        sd = (C.CloudDesc * 1)(C.CloudDesc(ps, 12, ps + 16, 12, len(sp)))
+        md = (C.CloudDesc * 1)(C.CloudDesc(pm, 12, pm + 16, 12, len(mp)))
+        dd = np.array([d], np.float32)
+        out = np.zeros((1, 1, 4, 4), np.float32)
+        status = np.zeros(1, np.int32)
+        C.check(C.lib.ppf_registration(sd, 1, md, 1, dd.ctypes.data, 2, 0.4, 0, 0, 0, 0, None, out.ctypes.data,
+                                       status.ctypes.data))
+        assert status[0] == 0 and (bits(out[0, 0]) == bits(want.pose)).all()
 
 
 def test_device_resident_clouds_match_host_clouds():
