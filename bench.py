@@ -373,6 +373,9 @@ def main():
                "ms_per_call": float(m.item()),
                "call": "host scene cloud -> H2D (every rank) -> ppf_model_lookup_sharded (prebuilt replicated model) -> host pose"}
 
+    cfg3 = None
+    if world > 1 and not args.no_configs:
+        cfg3 = config3(ppf, torch, load_synth(), comm, world)          # every rank makes the same call
     if rank == 0:
         hbm_peak, hbm_src = measured_peaks()
         # dominant kernel: the vote kernel.  Its unit of work is one vote = one shared-memory atomic increment of a
@@ -425,6 +428,8 @@ def main():
                                 "ms_step": [round(x, 3) for x in per_rank[:, 1].tolist()],
                                 "votes_per_step": [int(x) for x in per_rank[:, 2].tolist()]}
             line["parity_sharded"] = parity_sharded
+            if cfg3 is not None:
+                line["configs"] = {"configs[3]": cfg3}
         if world == 1 and not args.no_configs:
             line["configs"] = other_configs(ppf, C, torch, args)
         if world == 1 and not args.no_cpu_baseline:
@@ -457,6 +462,31 @@ def check_sharded_parity(ppf, C, comm, lookup_sharded):
           and (one.pose.view(np.uint32) == sh.pose.view(np.uint32)).all())
     lk.close(); sc.close(); m.close()
     return bool(ok)
+
+
+def config3(ppf, torch, synth, comm, world):
+    """BASELINE configs[3]: multi-model database -- 20 models against one 200k-point scene through ppf_registration
+    (host clouds in, poses out, model builds inside); with `comm` through ppf_registration_sharded, the scene
+    reference points sharded over the ranks.  One call (tens of seconds on one GPU)."""
+    rng = np.random.default_rng(SEED + 30)
+    models = [synth.make_model(1500 + 100 * (i % 6), seed=SEED + 31 + i) for i in range(20)]
+    sp0, sn0, T3 = synth.make_scene(models[0][0], models[0][1], 20000, seed=SEED + 60)
+    lp, ln = synth.make_lattice_scene(180000, pitch=1.5)
+    sp3 = np.concatenate([sp0, lp + sp0.min(0)]).astype(np.float32); sn3 = np.concatenate([sn0, ln]).astype(np.float32)
+    perm = rng.permutation(len(sp3)); sp3, sn3 = sp3[perm], sn3[perm]
+    dd = [synth.d_dist_for(p, TAU_D) for p, _ in models]
+    torch.cuda.synchronize(); t = time.perf_counter()
+    poses, status = ppf.ppf_registration([(sp3, sn3)], models, dd, 8, 0.4, comm=comm)
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t) * 1e3
+    R = (len(sp3) + 7) // 8
+    return {"workload": "20 models (1.5k-2k points each) x one 200k-point scene (object 0 planted + room lattice), "
+                        f"ref_point_df=8, one ppf_registration{'_sharded' if comm is not None else ''} call on {world} GPU(s) "
+                        "(model builds inside)",
+            "ms_per_scene": ms, "pairs_per_s": 20 * R * len(sp3) / (ms * 1e-3),
+            "planted_model_translation_error": float(np.linalg.norm(poses[0, 0, :3, 3] - T3[:3, 3])),
+            "status_ok": int((status == 0).sum()),
+            "poses_checksum": int(np.ascontiguousarray(poses).view(np.uint32).astype(np.uint64).sum())}
 
 
 def other_configs(ppf, C, torch, args):
@@ -508,26 +538,7 @@ def other_configs(ppf, C, torch, args):
                          "ceiling": "76 B per model pair (SURVEY 8d) at the measured HBM bandwidth"}
 
     # configs[3] on one GPU: 20 models against one 200k-point scene through ppf_registration (host clouds in, poses out)
-    rng = np.random.default_rng(SEED + 30)
-    models = [synth.make_model(1500 + 100 * (i % 6), seed=SEED + 31 + i) for i in range(20)]
-    sp0, sn0, T3 = synth.make_scene(models[0][0], models[0][1], 20000, seed=SEED + 60)
-    lp, ln = synth.make_lattice_scene(180000, pitch=1.5)
-    sp3 = np.concatenate([sp0, lp + sp0.min(0)]).astype(np.float32); sn3 = np.concatenate([sn0, ln]).astype(np.float32)
-    perm = rng.permutation(len(sp3)); sp3, sn3 = sp3[perm], sn3[perm]
-    dd = [synth.d_dist_for(p, TAU_D) for p, _ in models]
-    ts = []
-    for i in range(1):                               # one call (tens of seconds): pools and clocks are warm from the steps above
-        torch.cuda.synchronize(); t = time.perf_counter()
-        poses, status = ppf.ppf_registration([(sp3, sn3)], models, dd, 8, 0.4)
-        torch.cuda.synchronize()
-        ts.append((time.perf_counter() - t) * 1e3)
-    R = (len(sp3) + 7) // 8
-    p50 = statistics.median(ts)
-    out["configs[3]"] = {"workload": "20 models (1.5k-2k points each) x one 200k-point scene (object 0 planted + room lattice), "
-                                     "ref_point_df=8, one ppf_registration call on ONE GPU (model builds inside)",
-                         "p50_ms_per_scene": p50, "pairs_per_s": 20 * R * len(sp3) / (p50 * 1e-3),
-                         "planted_model_translation_error": float(np.linalg.norm(poses[0, 0, :3, 3] - T3[:3, 3])),
-                         "status_ok": int((status == 0).sum())}
+    out["configs[3]"] = config3(ppf, torch, synth, None, 1)
 
     # configs[4]: dense KinFu-scale scene -- 1M points (room lattice + one object), 2k-point model
     mp, mn = synth.make_model(2000, seed=0xD209)

@@ -272,10 +272,11 @@ class Model:
 
 def ppf_registration(scene_clouds, model_clouds, model_d_dists, ref_point_downsample_factor=1,
                      vote_count_threshold=0.4, cpu_clustering=False, use_l1_norm=False,
-                     use_averaged_clusters=False, devUse=0, model_weights=None):
+                     use_averaged_clusters=False, devUse=0, model_weights=None, comm=None):
     """ppf_registration (ppf.h:9-15).  ``scene_clouds`` / ``model_clouds`` are lists of
     (points[N,3], normals[N,3]) host arrays; returns float32 [num_scenes, num_models, 4, 4] and the
-    per-pair status codes."""
+    per-pair status codes.  With ``comm`` (dist.Comm) every rank makes the same call and the scene reference points
+    are sharded over the ranks (ppf_registration_sharded): same poses on every rank."""
     keep = []
 
     def descs(clouds):
@@ -291,6 +292,12 @@ def ppf_registration(scene_clouds, model_clouds, model_d_dists, ref_point_downsa
     dd = np.ascontiguousarray(model_d_dists, np.float32)
     poses = np.zeros((len(scene_clouds), len(model_clouds), 4, 4), np.float32)
     status = np.zeros((len(scene_clouds), len(model_clouds)), np.int32)
+    if comm is not None:
+        C.check(C.lib.ppf_registration_sharded(sd, len(scene_clouds), md, len(model_clouds), dd.ctypes.data,
+                                               int(ref_point_downsample_factor), float(vote_count_threshold),
+                                               int(cpu_clustering), int(use_l1_norm), int(use_averaged_clusters),
+                                               comm._h, poses.ctypes.data, status.ctypes.data))
+        return poses, status
     C.check(C.lib.ppf_registration(sd, len(scene_clouds), md, len(model_clouds), dd.ctypes.data,
                                    int(ref_point_downsample_factor), float(vote_count_threshold),
                                    int(cpu_clustering), int(use_l1_norm), int(use_averaged_clusters), int(devUse),

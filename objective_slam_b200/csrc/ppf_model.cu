@@ -23,6 +23,7 @@
 
 #include "../../include/ppf_b200.h"
 #include "ppf_internal.cuh"
+#include "ppf_radix.cuh"
 
 namespace ppf {
 
@@ -341,25 +342,39 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
 // ---------------------------------------------------------------------------------
 // Model table build
 // ---------------------------------------------------------------------------------
-// One thread per ordered model pair p = m_r*N + m_i (coalesced along m_i):
-//   key[p] = FNV-1a of the quantised feature (0 for the self pair)   -- ppf_kernel + ppf_hash_kernel
-//   idx[p] = p                                                          -- the sort's payload (hashkeyToDataMap)
-__global__ void __launch_bounds__(256) model_pairs_kernel(const float4 *__restrict__ pos,
+// The reference sorts all N^2 (FNV key, pair index) records with a 32-bit radix sort (Model::Model, model.cu:53-60;
+// ParallelHashArray, parallel_hash_array.hpp:55-77).  A model has only a few thousand distinct keys -- one per occupied
+// cell of the quantised feature space -- so the table is built by sorting the pairs by BUCKET RANK instead:
+//   1. model_cells_kernel: pair -> cell code (the quantised feature itself, no hash);           4 B / pair written
+//   2. mark_cells_kernel: which cells occur;  cell_keys_kernel: FNV key of every occupied cell (a few thousand hashes)
+//   3. sort + unique of those few thousand keys -> hashkeys[U] (cells whose keys collide share a bucket, as in the
+//      reference, where only the key is compared), cell_table_kernel -> cell -> bucket rank;
+//   4. pair_ranks_kernel: pair -> rank (one L2-resident table read), pair index as payload;     4 B read, 8 B written
+//   5. stable LSD radix sort over ceil(log2 U) bits (13 for a 10k-point model: 2 passes instead of 4) -> map;
+//   6. bucket_bounds_kernel: first / counts from the rank boundaries of the sorted run.         4 B / pair read
+// The arrays are bit-identical to the reference's: ranks ascend with the keys and the sort is stable in the pair index.
+constexpr uint32_t kKey0Cell = 0xFFFFFFFFu;           // cell code of a pair whose key is 0 (self pair, NaN distance)
+
+// One thread per ordered model pair p = m_r*N + m_i (coalesced along m_i): codes[p] = kd * 17^3 + cell of the three
+// angle bins (ppf_kernel + the quantiser of ppf_hash_kernel; the hash itself is taken per CELL afterwards).
+__global__ void __launch_bounds__(256) model_cells_kernel(const float4 *__restrict__ pos,
                                                           const float4 *__restrict__ nrm, int n, float d_dist,
-                                                          float inv_d, uint32_t *keys, uint32_t *idx, int *max_kd) {
+                                                          float inv_d, uint32_t *codes, int *max_kd) {
     size_t total = (size_t)n * n;
     int local_max = -1;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
         int r = (int)(p / n), i = (int)(p - (size_t)r * n);
-        uint32_t key = 0;
+        uint32_t code = kKey0Cell;
         if (r != i) {
             PointN a = load_point(pos, nrm, r), b = load_point(pos, nrm, i);
             FeatureBins fb = pair_feature_bins(a, b, d_dist, inv_d);
-            key = feature_key(fb.kd, fb.k1, fb.k2, fb.k3, d_dist);
-            if (fb.kd >= 0) local_max = max(local_max, fb.kd);
+            if (fb.kd >= 0) {
+                local_max = max(local_max, fb.kd);
+                // kd >= 65536 (d_dist absurdly small for this model) is refused by the host; keep the code in range
+                code = cell_index(min(fb.kd, 65535), fb.k1, fb.k2, fb.k3);
+            }
         }
-        keys[p] = key;
-        idx[p] = (uint32_t)p;
+        codes[p] = code;
     }
     local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 16));
     local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 8));
@@ -367,6 +382,66 @@ __global__ void __launch_bounds__(256) model_pairs_kernel(const float4 *__restri
     local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 2));
     local_max = max(local_max, __shfl_xor_sync(0xffffffffu, local_max, 1));
     if ((threadIdx.x & 31) == 0 && local_max >= 0) atomicMax(max_kd, local_max);
+}
+
+// occ[cell] = 1 for every cell a pair falls into (plain stores: all writers store the same value)
+__global__ void __launch_bounds__(256) mark_cells_kernel(const uint32_t *__restrict__ codes, size_t total, uint32_t *occ) {
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = codes[p];
+        if (c != kKey0Cell && occ[c] == 0u) occ[c] = 1u;
+    }
+}
+
+// (key, cell) of every occupied cell, in any order; slot 0 is the key-0 pseudo cell (the self pairs always exist)
+__global__ void cell_keys_kernel(const uint32_t *__restrict__ occ, int K_d, float d_dist, uint32_t *keys, uint32_t *cells,
+                                 uint32_t *count) {
+    const int total = K_d * kCellsPerDist;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { keys[0] = 0u; cells[0] = kKey0Cell; }
+    for (int cidx = blockIdx.x * blockDim.x + threadIdx.x; cidx < total; cidx += gridDim.x * blockDim.x) {
+        if (!occ[cidx]) continue;
+        int k3 = cidx % kAngleCells, t = cidx / kAngleCells;
+        int k2 = t % kAngleCells; t /= kAngleCells;
+        int k1 = t % kAngleCells; int kd = t / kAngleCells;
+        const uint32_t slot = 1u + atomicAdd(count, 1u);
+        keys[slot] = feature_key(kd, k1, k2, k3, d_dist);
+        cells[slot] = (uint32_t)cidx;
+    }
+}
+
+// sorted occupied-cell keys -> hashkeys (one per distinct key).  heads[i] = inclusive count of distinct keys up to i.
+__global__ void key_heads_kernel(const uint32_t *__restrict__ keys, uint32_t n, uint32_t *heads) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        heads[i] = (i == 0 || keys[i] != keys[i - 1]) ? 1u : 0u;
+}
+__global__ void unique_keys_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ ranks1, uint32_t n,
+                                   uint32_t *hashkeys) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        if (i == 0 || keys[i] != keys[i - 1]) hashkeys[ranks1[i] - 1u] = keys[i];
+}
+
+// codes[p] -> bucket rank (in place) + the sort's payload idx[p] = p (hashkeyToDataMap)
+__global__ void __launch_bounds__(256) pair_ranks_kernel(uint32_t *codes, const uint32_t *__restrict__ cell2bucket,
+                                                         size_t total, uint32_t *idx) {
+    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t c = codes[p];
+        // key 0 (self pair, NaN distance, or a cell whose FNV key happens to be 0) is the smallest key: rank 0
+        const uint32_t r = (c == kKey0Cell) ? 0u : __ldg(cell2bucket + c);
+        codes[p] = (r == kNoBucket) ? 0u : r;
+        idx[p] = (uint32_t)p;
+    }
+}
+
+// first[r] = where rank r starts in the sorted run; counts from the differences (every rank occurs)
+__global__ void __launch_bounds__(256) bucket_bounds_kernel(const uint32_t *__restrict__ ranks_sorted, size_t total,
+                                                            uint32_t *first) {
+    for (size_t q = blockIdx.x * (size_t)blockDim.x + threadIdx.x; q < total; q += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = ranks_sorted[q];
+        if (q == 0 || ranks_sorted[q - 1] != r) first[r] = (uint32_t)q;
+    }
+}
+__global__ void bucket_counts_kernel(const uint32_t *__restrict__ first, uint32_t U, uint32_t total, uint32_t *counts) {
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < U; r += gridDim.x * blockDim.x)
+        counts[r] = (r + 1u < U ? first[r + 1u] : total) - first[r];
 }
 
 // entries[q] = [theta : 20 | slow : 1 | m_r - chunk_base : 11] for sorted position q, where theta = 20-bit binary
@@ -583,55 +658,111 @@ int model_build(ModelTable &m) {
 
     // All build temporaries live in ONE scratch allocation (one cudaMalloc + one cudaFree per build:
     // allocator calls, not kernels, dominate the build time of a small model).
-    size_t sort_tmp = 0, rle_tmp = 0, scan_tmp = 0;
+    size_t sort_tmp = 0;
     PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                                  (uint32_t *)nullptr, (uint32_t *)nullptr, total));
-    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(nullptr, rle_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr,
-                                                    (uint32_t *)nullptr, (uint32_t *)nullptr, total));
-    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(nullptr, scan_tmp, (uint32_t *)nullptr, (uint32_t *)nullptr, total));
-    const size_t cub_tmp = std::max(sort_tmp, std::max(rle_tmp, scan_tmp));
+    {   // + the scan / sort of the occupied-cell keys (at most total + 1 records) and the scratch of the own radix sort
+        size_t t1 = 0, t2 = 0;
+        PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, (uint32_t *)nullptr, (uint32_t *)nullptr,
+                                                     (uint32_t *)nullptr, (uint32_t *)nullptr, total + 1));
+        PPF_CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, t2, (uint32_t *)nullptr, (uint32_t *)nullptr, total + 1));
+        sort_tmp = std::max(std::max(sort_tmp, std::max(t1, t2)), radix_plan(total, 32).scratch_words * 4) + 256;
+    }
     Workspace ws;
-    int rc = ws.reserve(3 * total * 4 + cub_tmp + 64);
+    int rc = ws.reserve(3 * total * 4 + sort_tmp + 1024);
     if (rc) return rc;
-    uint32_t *keys = ws.take<uint32_t>(total);
-    uint32_t *keys_sorted = ws.take<uint32_t>(total), *iota = ws.take<uint32_t>(total);
-    uint32_t *d_U = ws.take<uint32_t>(1);
+    uint32_t *ranks = ws.take<uint32_t>(total);                      // cell codes, then bucket ranks
+    uint32_t *ranks_sorted = ws.take<uint32_t>(total), *iota = ws.take<uint32_t>(total);
+    uint32_t *d_nocc = ws.take<uint32_t>(1);
     int *d_maxkd = ws.take<int>(1);
-    void *tmp = ws.take_bytes(cub_tmp);
+    void *tmp = ws.take_bytes(sort_tmp);
     struct Release { Workspace &w; ~Release() { w.release(); } } release_on_exit{ws};
-    if (!keys || !keys_sorted || !iota || !d_U || !d_maxkd || !tmp) {
+    if (!ranks || !ranks_sorted || !iota || !d_nocc || !d_maxkd || !tmp) {
         set_last_error("model: scratch arena too small");
         return PPF_ERR_CUDA;
     }
     PPF_CUDA_TRY(cudaMemsetAsync(d_maxkd, 0xFF, 4, cur_stream()));
+    PPF_CUDA_TRY(cudaMemsetAsync(d_nocc, 0, 4, cur_stream()));
     int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-    model_pairs_kernel<<<grid, 256, 0, cur_stream()>>>(m.cloud.pos, m.cloud.nrm, n, m.d_dist, m.inv_d_dist, keys, iota, d_maxkd);
+    model_cells_kernel<<<grid, 256, 0, cur_stream()>>>(m.cloud.pos, m.cloud.nrm, n, m.d_dist, m.inv_d_dist, ranks, d_maxkd);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
-
-    // sort (key, pair index): LSD radix sort, stable, so every bucket ascends in pair index
-    m.map = (uint32_t *)pool_alloc(total * 4, &m.map_cap);      // the two N^2 arrays come from the block cache
-    if (!m.map) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
-    PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, keys, keys_sorted, iota, m.map, total, 0, 32, cur_stream()));
-
-    // run-length encode -> unique keys + counts (histogram(), util.hpp:30-52); scan -> first index.
-    // keys / iota are dead after the sort and are reused as the RLE outputs.
-    uint32_t *uk = keys, *uc = iota;
-    PPF_CUDA_TRY(cub::DeviceRunLengthEncode::Encode(tmp, rle_tmp, keys_sorted, uk, uc, d_U, total, cur_stream()));
     int h_maxkd = -1;
-    PPF_CUDA_TRY(memcpy_sync(&m.U, d_U, 4, cudaMemcpyDeviceToHost));
     PPF_CUDA_TRY(memcpy_sync(&h_maxkd, d_maxkd, 4, cudaMemcpyDeviceToHost));
     if (h_maxkd >= 65536) {
         set_last_error("model: d_dist is more than 65536x smaller than the model extent");
         return PPF_ERR_UNSUPPORTED;
     }
     m.K_d = h_maxkd + 1;
-    PPF_CUDA_TRY(pooled_malloc(&m.hashkeys, (size_t)m.U * 4));
-    PPF_CUDA_TRY(pooled_malloc(&m.counts, (size_t)m.U * 4));
-    PPF_CUDA_TRY(pooled_malloc(&m.first, (size_t)m.U * 4));
-    PPF_CUDA_TRY(cudaMemcpyAsync(m.hashkeys, uk, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, cur_stream()));
-    PPF_CUDA_TRY(cudaMemcpyAsync(m.counts, uc, (size_t)m.U * 4, cudaMemcpyDeviceToDevice, cur_stream()));
-    PPF_CUDA_TRY(cub::DeviceScan::ExclusiveSum(tmp, scan_tmp, m.counts, m.first, m.U, cur_stream()));
+
+    // occupied cells -> their keys -> unique sorted keys = hashkeys.  (The cell table doubles as the occupancy map.)
+    const size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
+    PPF_CUDA_TRY(pooled_malloc(&m.cell2bucket, ncell * 4));
+    PPF_CUDA_TRY(cudaMemsetAsync(m.cell2bucket, 0, ncell * 4, cur_stream()));
+    mark_cells_kernel<<<grid, 256, 0, cur_stream()>>>(ranks, total, m.cell2bucket);
+    count_launch();
+    // the (key, cell) lists of the occupied cells: at most min(ncell, total) + 1 records, four arrays
+    const size_t occ_cap = std::min(ncell, total) + 1;
+    uint32_t *clists = nullptr;
+    PPF_CUDA_TRY(pooled_malloc(&clists, 4 * occ_cap * sizeof(uint32_t)));
+    struct FreeLists { uint32_t *p; ~FreeLists() { pooled_free(p); } } free_lists{clists};
+    uint32_t *ckeys = clists, *ccells = clists + occ_cap, *ckeys_s = clists + 2 * occ_cap, *ccells_s = clists + 3 * occ_cap;
+    cell_keys_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(
+        m.cell2bucket, m.K_d, m.d_dist, ckeys, ccells, d_nocc);
+    count_launch();
+    PPF_CUDA_TRY(cudaGetLastError());
+    uint32_t n_occ = 0;
+    PPF_CUDA_TRY(memcpy_sync(&n_occ, d_nocc, 4, cudaMemcpyDeviceToHost));
+    n_occ += 1;                                                      // + the key-0 pseudo cell
+    {
+        // a few thousand records: library sort + scan (0.01% of the build's bytes)
+        size_t t1 = 0, t2 = 0;
+        PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(nullptr, t1, ckeys, ckeys_s, ccells, ccells_s, n_occ));
+        PPF_CUDA_TRY(cub::DeviceScan::InclusiveSum(nullptr, t2, ckeys, ckeys, n_occ));
+        if (std::max(t1, t2) > sort_tmp) { set_last_error("model: scratch arena too small"); return PPF_ERR_CUDA; }
+        PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, t1, ckeys, ckeys_s, ccells, ccells_s, n_occ, 0, 32, cur_stream()));
+        const int g2 = (int)std::min<size_t>((n_occ + 255) / 256, 148 * 8);
+        key_heads_kernel<<<g2, 256, 0, cur_stream()>>>(ckeys_s, n_occ, ckeys);           // ckeys reused: heads, then 1-based ranks
+        PPF_CUDA_TRY(cub::DeviceScan::InclusiveSum(tmp, t2, ckeys, ckeys, n_occ, cur_stream()));
+        PPF_CUDA_TRY(memcpy_sync(&m.U, ckeys + (n_occ - 1), 4, cudaMemcpyDeviceToHost));
+        PPF_CUDA_TRY(pooled_malloc(&m.hashkeys, (size_t)m.U * 4));
+        PPF_CUDA_TRY(pooled_malloc(&m.counts, (size_t)m.U * 4));
+        PPF_CUDA_TRY(pooled_malloc(&m.first, (size_t)m.U * 4));
+        unique_keys_kernel<<<g2, 256, 0, cur_stream()>>>(ckeys_s, ckeys, n_occ, m.hashkeys);
+        count_launch(3);
+    }
+    // cell -> bucket (also for unoccupied cells whose key collides with a model key: they vote in the reference)
+    cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(m.hashkeys, m.U, m.K_d,
+                                                                                   m.d_dist, m.cell2bucket);
+    count_launch();
+    PPF_CUDA_TRY(cudaGetLastError());
+
+    // pairs -> ranks; stable radix sort over the rank bits only (ppf_radix.cuh); every bucket ascends in pair index
+    m.map = (uint32_t *)pool_alloc(total * 4, &m.map_cap);      // the two N^2 arrays come from the block cache
+    if (!m.map) { set_last_error("model: out of device memory"); return PPF_ERR_CUDA; }
+    int rank_bits = 1;
+    while (rank_bits < 32 && (1ull << rank_bits) < (unsigned long long)m.U) rank_bits++;
+    const RadixPlan plan = radix_plan(total, rank_bits);
+    const bool library_sort = getenv("PPF_B200_SORT") && !strcmp(getenv("PPF_B200_SORT"), "cub");   // A/B hook
+    uint32_t *rk[2] = {ranks, ranks_sorted};
+    // the sorted payload must land in m.map: with an even number of passes the payload starts there
+    uint32_t *pv[2] = {iota, m.map};
+    if (!library_sort && (plan.passes & 1) == 0) { pv[0] = m.map; pv[1] = iota; }
+    pair_ranks_kernel<<<grid, 256, 0, cur_stream()>>>(ranks, m.cell2bucket, total, pv[0]);
+    count_launch();
+    const uint32_t *ranks_final = ranks_sorted;
+    if (library_sort) {
+        PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, ranks, ranks_sorted, iota, m.map, total, 0, rank_bits, cur_stream()));
+    } else {
+        if (plan.scratch_words * 4 > sort_tmp) { set_last_error("model: scratch arena too small"); return PPF_ERR_CUDA; }
+        count_launch(radix_sort_pairs(rk, pv, total, plan, (uint32_t *)tmp, cur_stream()));
+        ranks_final = rk[plan.passes & 1];
+    }
+    PPF_CUDA_TRY(cudaGetLastError());
+    bucket_bounds_kernel<<<grid, 256, 0, cur_stream()>>>(ranks_final, total, m.first);
+    bucket_counts_kernel<<<(int)std::min<size_t>(((size_t)m.U + 255) / 256, 148 * 8), 256, 0, cur_stream()>>>(m.first, m.U, (uint32_t)total, m.counts);
+    count_launch(2);
+    PPF_CUDA_TRY(cudaGetLastError());
 
     // Accumulator chunk geometry = which vote kernel serves this table.  The grouped kernel (small chunks,
     // big hit queue: ppf_vote_grouped.cu) wins when voting dominates, i.e. when buckets are long (10k-point
@@ -667,14 +798,6 @@ int model_build(ModelTable &m) {
         size_t t = (size_t)m.U * m.n_chunks;
         chunk_ranges_kernel<<<(int)std::min<size_t>((t + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(
             m.map, m.first, m.counts, m.U, n, m.chunk_rows, m.n_chunks, m.ranges);
-        count_launch();
-    }
-    PPF_CUDA_TRY(cudaGetLastError());
-    size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
-    PPF_CUDA_TRY(pooled_malloc(&m.cell2bucket, ncell * 4));
-    if (m.K_d > 0) {
-        cell_table_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(m.hashkeys, m.U, m.K_d,
-                                                                                       m.d_dist, m.cell2bucket);
         count_launch();
     }
     PPF_CUDA_TRY(cudaGetLastError());
