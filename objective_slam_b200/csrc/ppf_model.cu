@@ -236,6 +236,15 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
     }
     const int grid = std::min((n + 255) / 256, 148 * 8);
     float *mm_dev = nullptr;
+    if (!spatial_sort) {
+        // model clouds: the AABB alone (bounds the distance bins of the model's pairs: sizes the cell map of the build)
+        float *mm = ws.take<float>(6);
+        mm_dev = mm;
+        const float init[6] = {3.0e38f, 3.0e38f, 3.0e38f, -3.0e38f, -3.0e38f, -3.0e38f};
+        PPF_CUDA_TRY(cudaMemcpyAsync(mm, init, sizeof(init), cudaMemcpyHostToDevice, cur_stream()));
+        bbox_kernel<<<grid, 256, 0, cur_stream()>>>(dx, xs, n, mm);
+        count_launch();
+    }
     if (spatial_sort) {
         float *mm = ws.take<float>(6);
         mm_dev = mm;
@@ -265,7 +274,7 @@ int cloud_create(const float *xyz, int xs, const float *nrm, int ns, int n, int 
         count_launch();
         PPF_CUDA_TRY(cudaGetLastError());
     }
-    if (spatial_sort && mm_dev) {                       // host copy of the AABB: bounds the distance bins of the scene's pairs
+    if (mm_dev) {                                       // host copy of the AABB: bounds the distance bins of the cloud's pairs
         float mm_h[6];
         PPF_CUDA_TRY(cudaMemcpyAsync(mm_h, mm_dev, sizeof(mm_h), cudaMemcpyDeviceToHost, cur_stream()));
         PPF_CUDA_TRY(cudaStreamSynchronize(cur_stream()));
@@ -345,21 +354,26 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
 // The reference sorts all N^2 (FNV key, pair index) records with a 32-bit radix sort (Model::Model, model.cu:53-60;
 // ParallelHashArray, parallel_hash_array.hpp:55-77).  A model has only a few thousand distinct keys -- one per occupied
 // cell of the quantised feature space -- so the table is built by sorting the pairs by BUCKET RANK instead:
-//   1. model_cells_kernel: pair -> cell code (the quantised feature itself, no hash);           4 B / pair written
-//   2. mark_cells_kernel: which cells occur;  cell_keys_kernel: FNV key of every occupied cell (a few thousand hashes)
-//   3. sort + unique of those few thousand keys -> hashkeys[U] (cells whose keys collide share a bucket, as in the
-//      reference, where only the key is compared), cell_table_kernel -> cell -> bucket rank;
-//   4. pair_ranks_kernel: pair -> rank (one L2-resident table read), pair index as payload;     4 B read, 8 B written
-//   5. stable LSD radix sort over ceil(log2 U) bits (13 for a 10k-point model: 2 passes instead of 4) -> map;
-//   6. bucket_bounds_kernel: first / counts from the rank boundaries of the sorted run.         4 B / pair read
+//   1. model_cells_kernel: pair -> cell code (the quantised feature itself, no hash) + a byte map of the cells that
+//      occur (sized from the cloud's bounding box);                                             4 B / pair written
+//   2. cell_keys_kernel: FNV key of every occupied cell (a few thousand hashes); sort + unique of those keys ->
+//      hashkeys[U] (cells whose keys collide share a bucket, as in the reference, where only the key is compared);
+//      cell_table_kernel: cell -> bucket rank;
+//   3. pair_ranks_kernel: code -> rank in place (one L2-resident table read);                   4 B read, 4 B written
+//      own stable LSD radix sort (ppf_radix.cuh) over ceil(log2 U) rank bits (13 for a 10k-point model: 2 passes
+//      instead of 4 over 32 key bits), the pair index as implicit payload of pass 0;    per pass 4 + 8 B read, 8 B written
+//   4. bucket_bounds_kernel: first / counts from the rank boundaries of the sorted run.         4 B / pair read
 // The arrays are bit-identical to the reference's: ranks ascend with the keys and the sort is stable in the pair index.
 constexpr uint32_t kKey0Cell = 0xFFFFFFFFu;           // cell code of a pair whose key is 0 (self pair, NaN distance)
 
 // One thread per ordered model pair p = m_r*N + m_i (coalesced along m_i): codes[p] = kd * 17^3 + cell of the three
 // angle bins (ppf_kernel + the quantiser of ppf_hash_kernel; the hash itself is taken per CELL afterwards).
+// occ[cell] = 1 for every cell a pair falls into (byte map sized from the cloud's bounding box: K_bound distance bins;
+// plain stores, all writers store the same value; the map is small enough to live in L1 / L2).
 __global__ void __launch_bounds__(256) model_cells_kernel(const float4 *__restrict__ pos,
                                                           const float4 *__restrict__ nrm, int n, float d_dist,
-                                                          float inv_d, uint32_t *codes, int *max_kd) {
+                                                          float inv_d, uint32_t *codes, int *max_kd, unsigned char *occ,
+                                                          int K_bound) {
     size_t total = (size_t)n * n;
     int local_max = -1;
     for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
@@ -372,6 +386,7 @@ __global__ void __launch_bounds__(256) model_cells_kernel(const float4 *__restri
                 local_max = max(local_max, fb.kd);
                 // kd >= 65536 (d_dist absurdly small for this model) is refused by the host; keep the code in range
                 code = cell_index(min(fb.kd, 65535), fb.k1, fb.k2, fb.k3);
+                if (fb.kd < K_bound && !occ[code]) occ[code] = 1;          // (kd >= K_bound: refused by the host)
             }
         }
         codes[p] = code;
@@ -384,16 +399,8 @@ __global__ void __launch_bounds__(256) model_cells_kernel(const float4 *__restri
     if ((threadIdx.x & 31) == 0 && local_max >= 0) atomicMax(max_kd, local_max);
 }
 
-// occ[cell] = 1 for every cell a pair falls into (plain stores: all writers store the same value)
-__global__ void __launch_bounds__(256) mark_cells_kernel(const uint32_t *__restrict__ codes, size_t total, uint32_t *occ) {
-    for (size_t p = blockIdx.x * (size_t)blockDim.x + threadIdx.x; p < total; p += (size_t)gridDim.x * blockDim.x) {
-        const uint32_t c = codes[p];
-        if (c != kKey0Cell && occ[c] == 0u) occ[c] = 1u;
-    }
-}
-
 // (key, cell) of every occupied cell, in any order; slot 0 is the key-0 pseudo cell (the self pairs always exist)
-__global__ void cell_keys_kernel(const uint32_t *__restrict__ occ, int K_d, float d_dist, uint32_t *keys, uint32_t *cells,
+__global__ void cell_keys_kernel(const unsigned char *__restrict__ occ, int K_d, float d_dist, uint32_t *keys, uint32_t *cells,
                                  uint32_t *count) {
     const int total = K_d * kCellsPerDist;
     if (blockIdx.x == 0 && threadIdx.x == 0) { keys[0] = 0u; cells[0] = kKey0Cell; }
@@ -427,7 +434,7 @@ __global__ void __launch_bounds__(256) pair_ranks_kernel(uint32_t *codes, const 
         // key 0 (self pair, NaN distance, or a cell whose FNV key happens to be 0) is the smallest key: rank 0
         const uint32_t r = (c == kKey0Cell) ? 0u : __ldg(cell2bucket + c);
         codes[p] = (r == kNoBucket) ? 0u : r;
-        idx[p] = (uint32_t)p;
+        if (idx) idx[p] = (uint32_t)p;
     }
 }
 
@@ -683,24 +690,37 @@ int model_build(ModelTable &m) {
     }
     PPF_CUDA_TRY(cudaMemsetAsync(d_maxkd, 0xFF, 4, cur_stream()));
     PPF_CUDA_TRY(cudaMemsetAsync(d_nocc, 0, 4, cur_stream()));
+    // distance bins a pair of this cloud can reach: longest pair <= diagonal of the AABB of the finite points
+    double diag2 = 0.0;
+    for (int k = 0; k < 3; k++) {
+        const double e = (double)m.cloud.bb_hi[k] - (double)m.cloud.bb_lo[k];
+        if (e > 0.0) diag2 += e * e;
+    }
+    const double kb = std::sqrt(diag2) * 1.0001 / (double)m.d_dist + 2.0;
+    if (!(kb < 65536.0)) {
+        set_last_error("model: d_dist is more than 65536x smaller than the model extent");
+        return PPF_ERR_UNSUPPORTED;
+    }
+    const int K_bound = (int)kb;
+    unsigned char *occ = nullptr;
+    PPF_CUDA_TRY(pooled_malloc(&occ, (size_t)K_bound * kCellsPerDist));
+    struct FreeOcc { unsigned char *p; ~FreeOcc() { pooled_free(p); } } free_occ{occ};
+    PPF_CUDA_TRY(cudaMemsetAsync(occ, 0, (size_t)K_bound * kCellsPerDist, cur_stream()));
     int grid = (int)std::min<size_t>((total + 255) / 256, 148 * 32);
-    model_cells_kernel<<<grid, 256, 0, cur_stream()>>>(m.cloud.pos, m.cloud.nrm, n, m.d_dist, m.inv_d_dist, ranks, d_maxkd);
+    model_cells_kernel<<<grid, 256, 0, cur_stream()>>>(m.cloud.pos, m.cloud.nrm, n, m.d_dist, m.inv_d_dist, ranks, d_maxkd, occ, K_bound);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     int h_maxkd = -1;
     PPF_CUDA_TRY(memcpy_sync(&h_maxkd, d_maxkd, 4, cudaMemcpyDeviceToHost));
-    if (h_maxkd >= 65536) {
-        set_last_error("model: d_dist is more than 65536x smaller than the model extent");
-        return PPF_ERR_UNSUPPORTED;
+    if (h_maxkd >= K_bound) {
+        set_last_error("model: a pair longer than the cloud's bounding box diagonal (internal error)");
+        return PPF_ERR_CUDA;
     }
     m.K_d = h_maxkd + 1;
 
-    // occupied cells -> their keys -> unique sorted keys = hashkeys.  (The cell table doubles as the occupancy map.)
+    // occupied cells -> their keys -> unique sorted keys = hashkeys
     const size_t ncell = (size_t)std::max(1, m.K_d) * kCellsPerDist;
     PPF_CUDA_TRY(pooled_malloc(&m.cell2bucket, ncell * 4));
-    PPF_CUDA_TRY(cudaMemsetAsync(m.cell2bucket, 0, ncell * 4, cur_stream()));
-    mark_cells_kernel<<<grid, 256, 0, cur_stream()>>>(ranks, total, m.cell2bucket);
-    count_launch();
     // the (key, cell) lists of the occupied cells: at most min(ncell, total) + 1 records, four arrays
     const size_t occ_cap = std::min(ncell, total) + 1;
     uint32_t *clists = nullptr;
@@ -708,7 +728,7 @@ int model_build(ModelTable &m) {
     struct FreeLists { uint32_t *p; ~FreeLists() { pooled_free(p); } } free_lists{clists};
     uint32_t *ckeys = clists, *ccells = clists + occ_cap, *ckeys_s = clists + 2 * occ_cap, *ccells_s = clists + 3 * occ_cap;
     cell_keys_kernel<<<(int)std::min<size_t>((ncell + 255) / 256, 148 * 32), 256, 0, cur_stream()>>>(
-        m.cell2bucket, m.K_d, m.d_dist, ckeys, ccells, d_nocc);
+        occ, m.K_d, m.d_dist, ckeys, ccells, d_nocc);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
     uint32_t n_occ = 0;
@@ -748,14 +768,19 @@ int model_build(ModelTable &m) {
     // the sorted payload must land in m.map: with an even number of passes the payload starts there
     uint32_t *pv[2] = {iota, m.map};
     if (!library_sort && (plan.passes & 1) == 0) { pv[0] = m.map; pv[1] = iota; }
-    pair_ranks_kernel<<<grid, 256, 0, cur_stream()>>>(ranks, m.cell2bucket, total, pv[0]);
-    count_launch();
     const uint32_t *ranks_final = ranks_sorted;
     if (library_sort) {
+        pair_ranks_kernel<<<grid, 256, 0, cur_stream()>>>(ranks, m.cell2bucket, total, pv[0]);
+        count_launch();
         PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, ranks, ranks_sorted, iota, m.map, total, 0, rank_bits, cur_stream()));
     } else {
+        // codes -> ranks in place; pass 0 takes the pair index as the payload, so no index array is written before the
+        // sort.  (Reading the codes THROUGH the cell table inside pass 0 was measured slower: the dependent gather
+        // sits on the critical path of a tile, 2.04 ms against 0.22 + 1.0 ms.)
         if (plan.scratch_words * 4 > sort_tmp) { set_last_error("model: scratch arena too small"); return PPF_ERR_CUDA; }
-        count_launch(radix_sort_pairs(rk, pv, total, plan, (uint32_t *)tmp, cur_stream()));
+        pair_ranks_kernel<<<grid, 256, 0, cur_stream()>>>(ranks, m.cell2bucket, total, nullptr);
+        count_launch();
+        count_launch(radix_sort_pairs(rk, pv, total, plan, (uint32_t *)tmp, cur_stream(), nullptr, true));
         ranks_final = rk[plan.passes & 1];
     }
     PPF_CUDA_TRY(cudaGetLastError());

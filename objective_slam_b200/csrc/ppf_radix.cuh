@@ -6,17 +6,28 @@
 // One pass = three launches:
 //   radix_hist_kernel     per tile of 8192 records: digit histogram (shared-memory atomics) -> tilehist[digit][tile]
 //   scan (3 small kernels) exclusive prefix over tilehist in (digit, tile) order = where the tile's records of a digit go
-//   radix_scatter_kernel  per tile: the 16 warps count their digits, a block scan turns the counts into cursors, then
-//                          every warp ranks its records in index order (match.any groups the lanes of a digit; the
-//                          group's leader advances the warp's cursor) into a shared-memory staging area sorted by
-//                          digit, which is written out in coalesced runs.  Stable: a warp owns a contiguous slice of
-//                          the tile and walks it in index order; warps and tiles are ordered by the prefix sums.
+//   radix_scatter_kernel  per tile: every warp ranks the records of its slice among those of the same digit, in index
+//                          order (match.any groups the lanes of a digit; the group's leader advances the warp's
+//                          count), a block scan turns the counts into offsets, the records go to a shared-memory
+//                          staging area sorted by digit and leave it in coalesced runs.  Stable: a warp owns a
+//                          contiguous slice of the tile; warps and tiles are ordered by the prefix sums.
 // HBM traffic per pass and record: 4 B (histogram) + 8 B read + 8 B written.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <cstdlib>
 
 namespace ppf {
+
+// Pass 0 may translate what it reads through a table (the model build sorts by bucket rank but has cell codes in
+// memory: rank = lut[code], code 0xFFFFFFFF and table value 0xFFFFFFFF -> rank 0) and may take the record's index as
+// its value (vals_in == nullptr): neither the ranks nor an iota array are then ever written.
+__device__ __forceinline__ uint32_t rx_key(const uint32_t *__restrict__ keys, size_t p, const uint32_t *__restrict__ lut) {
+    const uint32_t c = keys[p];
+    if (!lut) return c;
+    const uint32_t r = (c == 0xFFFFFFFFu) ? 0u : __ldg(lut + c);
+    return (r == 0xFFFFFFFFu) ? 0u : r;
+}
 
 constexpr int kRxThreads = 512;
 constexpr int kRxItems   = 16;
@@ -24,8 +35,9 @@ constexpr int kRxTile    = kRxThreads * kRxItems;      // 8192 records per CTA
 constexpr int kRxMaxBins = 256;
 constexpr int kRxWarps   = kRxThreads / 32;
 
-__global__ void __launch_bounds__(kRxThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, size_t n, int shift,
-                                                                uint32_t mask, uint32_t ntiles, uint32_t *tilehist) {
+__global__ void __launch_bounds__(kRxThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ lut,
+                                                                size_t n, int shift, uint32_t mask, uint32_t ntiles,
+                                                                uint32_t *tilehist) {
     __shared__ uint32_t hist[kRxMaxBins];
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         for (int i = threadIdx.x; i <= (int)mask; i += kRxThreads) hist[i] = 0;
@@ -34,7 +46,7 @@ __global__ void __launch_bounds__(kRxThreads) radix_hist_kernel(const uint32_t *
 #pragma unroll
         for (int j = 0; j < kRxItems; j++) {
             const size_t p = base + (size_t)j * kRxThreads + threadIdx.x;
-            if (p < n) atomicAdd(&hist[(keys[p] >> shift) & mask], 1u);
+            if (p < n) atomicAdd(&hist[(rx_key(keys, p, lut) >> shift) & mask], 1u);
         }
         __syncthreads();
         for (int i = threadIdx.x; i <= (int)mask; i += kRxThreads) tilehist[(size_t)i * ntiles + tile] = hist[i];
@@ -108,6 +120,7 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *a, s
 
 // ---- scatter ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kRxThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
+                                                                   const uint32_t *__restrict__ lut,
                                                                    const uint32_t *__restrict__ vals_in, size_t n, int shift,
                                                                    uint32_t mask, uint32_t ntiles,
                                                                    const uint32_t *__restrict__ tileoff,
@@ -124,22 +137,29 @@ __global__ void __launch_bounds__(kRxThreads) radix_scatter_kernel(const uint32_
     const unsigned lt = (1u << lane) - 1u;
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t base = (size_t)tile * kRxTile + (size_t)warp * (kRxItems * 32) + lane;      // warp-blocked slices
-        uint32_t k[kRxItems], v[kRxItems];
+        uint32_t k[kRxItems], v[kRxItems], lpos[kRxItems];
         for (uint32_t i = threadIdx.x; i < kRxWarps * nb; i += kRxThreads) cursor[i] = 0;
 #pragma unroll
         for (int j = 0; j < kRxItems; j++) {
             const size_t p = base + (size_t)j * 32;
-            k[j] = p < n ? keys_in[p] : 0u;
-            v[j] = p < n ? vals_in[p] : 0u;
+            k[j] = p < n ? rx_key(keys_in, p, lut) : 0u;
+            v[j] = p < n ? (vals_in ? vals_in[p] : (uint32_t)p) : 0u;
         }
         __syncthreads();
-        // 1: digit counts per warp
+        // 1: every warp ranks its records among the records of the same digit in its slice, in index order:
+        //    match.any groups the lanes of a digit, the group's leader advances the warp's count
         uint32_t *mine = cursor + warp * nb;
 #pragma unroll
         for (int j = 0; j < kRxItems; j++) {
             const size_t p = base + (size_t)j * 32;
             const uint32_t d = p < n ? ((k[j] >> shift) & mask) : mask + 1u;
-            atomicAdd(&mine[d], 1u);
+            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs((int)peers) - 1;
+            uint32_t old = 0;
+            if (lane == leader) { old = mine[d]; mine[d] = old + (uint32_t)__popc(peers); }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            lpos[j] = old + (uint32_t)__popc(peers & lt);
+            __syncwarp();
         }
         __syncthreads();
         // 2: counts -> cursors.  Thread d < nb owns digit d: prefix over the warps, then over the digits.
@@ -176,19 +196,13 @@ __global__ void __launch_bounds__(kRxThreads) radix_scatter_kernel(const uint32_
             }
         }
         __syncthreads();
-        // 3: stable ranking, in index order within the warp's slice
+        // 3: into the staging area, sorted by digit (stable: warps and tiles are ordered by the prefix sums)
 #pragma unroll
         for (int j = 0; j < kRxItems; j++) {
             const size_t p = base + (size_t)j * 32;
             const uint32_t d = p < n ? ((k[j] >> shift) & mask) : mask + 1u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
-            const int leader = __ffs((int)peers) - 1;
-            uint32_t old = 0;
-            if (lane == leader) { old = mine[d]; mine[d] = old + (uint32_t)__popc(peers); }
-            old = __shfl_sync(0xffffffffu, old, leader);
-            const uint32_t slot = old + (uint32_t)__popc(peers & lt);
+            const uint32_t slot = mine[d] + lpos[j];
             skey[slot] = k[j]; sval[slot] = v[j];
-            __syncwarp();
         }
         __syncthreads();
         // 4: coalesced runs out of the staging area
@@ -217,6 +231,10 @@ inline RadixPlan radix_plan(size_t n, int bits) {
     const int per = (bits + pl.passes - 1) / pl.passes;
     int left = bits;
     for (int i = 0; i < pl.passes; i++) { pl.pass_bits[i] = left < per ? left : per; left -= pl.pass_bits[i]; }
+    if (const char *e = getenv("PPF_B200_RADIX_FIRST")) {          // experiment hook: bits of pass 0 (two-pass plans only)
+        const int f = atoi(e);
+        if (pl.passes == 2 && f >= 1 && f <= 8 && bits - f >= 1 && bits - f <= 8) { pl.pass_bits[0] = f; pl.pass_bits[1] = bits - f; }
+    }
     pl.ntiles = (uint32_t)((n + kRxTile - 1) / kRxTile);
     const size_t hist = (size_t)kRxMaxBins * pl.ntiles;
     pl.scratch_words = hist + (hist + kScanBlock - 1) / kScanBlock + 16;
@@ -226,7 +244,7 @@ inline RadixPlan radix_plan(size_t n, int bits) {
 // Sorts (keys[0], vals[0]) by the low `bits` key bits; the buffers ping-pong, the result lands in
 // keys[passes & 1] / vals[passes & 1].  `scratch` holds radix_plan(n, bits).scratch_words u32.  Returns the launches.
 inline int radix_sort_pairs(uint32_t *keys[2], uint32_t *vals[2], size_t n, const RadixPlan &pl, uint32_t *scratch,
-                            cudaStream_t stream) {
+                            cudaStream_t stream, const uint32_t *lut = nullptr, bool index_values = false) {
     int launches = 0, shift = 0, cur = 0;
     uint32_t *tilehist = scratch;
     for (int pass = 0; pass < pl.passes; pass++) {
@@ -235,13 +253,15 @@ inline int radix_sort_pairs(uint32_t *keys[2], uint32_t *vals[2], size_t n, cons
         uint32_t *bsum = scratch + (size_t)kRxMaxBins * pl.ntiles;
         const uint32_t nblk = (uint32_t)((hist_n + kScanBlock - 1) / kScanBlock);
         const unsigned grid = pl.ntiles < 148u * 8u ? pl.ntiles : 148u * 8u;
-        radix_hist_kernel<<<grid, kRxThreads, 0, stream>>>(keys[cur], n, shift, mask, pl.ntiles, tilehist);
+        const uint32_t *lut0 = pass == 0 ? lut : nullptr;
+        const uint32_t *vin = (pass == 0 && index_values) ? nullptr : vals[cur];
+        radix_hist_kernel<<<grid, kRxThreads, 0, stream>>>(keys[cur], lut0, n, shift, mask, pl.ntiles, tilehist);
         scan_block_sums_kernel<<<nblk, kScanThreads, 0, stream>>>(tilehist, hist_n, bsum);
         scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(bsum, nblk);
         scan_apply_kernel<<<nblk, kScanThreads, 0, stream>>>(tilehist, hist_n, bsum);
         const size_t smem = ((size_t)(kRxWarps + 2) * (mask + 2u) + 2u * kRxTile) * sizeof(uint32_t);
         cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        radix_scatter_kernel<<<grid, kRxThreads, smem, stream>>>(keys[cur], vals[cur], n, shift, mask, pl.ntiles, tilehist,
+        radix_scatter_kernel<<<grid, kRxThreads, smem, stream>>>(keys[cur], lut0, vin, n, shift, mask, pl.ntiles, tilehist,
                                                                  keys[cur ^ 1], vals[cur ^ 1]);
         launches += 5;
         shift += pl.pass_bits[pass];
