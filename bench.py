@@ -86,18 +86,18 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for s in self.samples:
             try:
-                sm.append(float(s[0])); mx.append(float(s[1]))
+                sm.append(float(s[0])); mx.append(float(s[1])); pw.append(float(s[2]))
                 for n, v in zip(names, s[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(n)
             except Exception:
                 pass
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w": statistics.median(pw) if pw else None, "samples": len(sm), "reasons": sorted(reasons)}
 
 
 def measured_peaks():
@@ -298,9 +298,8 @@ def main():
         res = step()
     grouped = model.layout()[2]
     atoms_per_clk, atoms_kind, atoms_src = measured_atoms_per_clk(grouped) if rank == 0 else (None, None, None)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
+    sampler = ClockSampler(local_rank)          # every rank samples ITS GPU: a slow rank is usually a slow clock
+    sampler.start()
     launches0 = C.lib.ppf_kernel_launch_count()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     vote_ms, pairs_local, votes_local = [], 0, 0
@@ -317,7 +316,11 @@ def main():
     # the library works on its own stream and every lookup ends synchronised (host pose out), so the torch events
     # bracket complete steps; ms_vote is the library's own CUDA-event time of the vote kernel on ITS stream
     step_ms = [a.elapsed_time(b) for a, b in ev]
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = sampler.stop()
+    clocks_all = [clocks]
+    if world > 1:
+        clocks_all = [None] * world
+        dist.all_gather_object(clocks_all, clocks)
 
     tot = torch.tensor([sum(step_ms), wall * 1e3, sum(vote_ms)], dtype=torch.float64, device=dev)
     cnt = torch.tensor([pairs_local, votes_local], dtype=torch.int64, device=dev)
@@ -424,7 +427,10 @@ def main():
                                          "mostly from L2), so HBM is not the bound and no HBM fraction is claimed"}},
         }
         if world > 1:
-            line["per_rank"] = {"ms_vote": [round(x, 3) for x in per_rank[:, 0].tolist()],
+            line["per_rank"] = {"sm_mhz": [c.get("sm_mhz") for c in clocks_all],
+                                "power_w": [c.get("power_w") for c in clocks_all],
+                                "reasons": [c.get("reasons") for c in clocks_all],
+                                "ms_vote": [round(x, 3) for x in per_rank[:, 0].tolist()],
                                 "ms_step": [round(x, 3) for x in per_rank[:, 1].tolist()],
                                 "votes_per_step": [int(x) for x in per_rank[:, 2].tolist()]}
             line["parity_sharded"] = parity_sharded

@@ -131,8 +131,23 @@ __global__ void cellhash_kernel(const float3 *trans, uint32_t *cell_hash, uint32
 // i.e. in exactly the order the reference's single thread visits them (neighbour cell 0..26, then
 // ascending pose index inside the cell) -- float addition is not associative once a score passes
 // 2^24, so the order is part of the result.
-__global__ void cluster_kernel(const float3 *trans_in, const float4 *quats, const float *weights,
-                               const uint32_t *adj_hash, const uint32_t *sorted_hash, const uint32_t *sorted_idx,
+// The neighbour poses are read from CELL-SORTED copies (sq / st = quaternion and (translation, weight) of the pose at
+// sorted position p, pose_gather_kernel): a dense cell is then one contiguous run of 16-byte records instead of three
+// gathers per candidate through sorted_idx (K = 396k survivors: the gathers were most of the kernel's time).
+__global__ void pose_gather_kernel(const uint32_t *__restrict__ sorted_idx, const float4 *__restrict__ quats,
+                                   const float3 *__restrict__ trans, const float *__restrict__ weights, int count,
+                                   float4 *sq, float4 *st) {
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < count; p += gridDim.x * blockDim.x) {
+        const uint32_t j = sorted_idx[p];
+        const float3 t = trans[j];
+        sq[p] = quats[j];
+        st[p] = make_float4(t.x, t.y, t.z, weights[j]);
+    }
+}
+
+__global__ void cluster_kernel(const float3 *trans_in, const float4 *quats, const float4 *__restrict__ sq,
+                               const float4 *__restrict__ st,
+                               const uint32_t *adj_hash, const uint32_t *sorted_hash,
                                float *scores, float3 *trans_out, int count, float trans_thresh, int use_l1_norm,
                                int use_averaged_clusters, int shard, int n_shards) {
     if (count <= 1) return;
@@ -163,12 +178,12 @@ __global__ void cluster_kernel(const float3 *trans_in, const float4 *quats, cons
                 float w = 0.f;
                 float3 tj = make_float3(0.f, 0.f, 0.f);
                 if (valid) {
-                    const uint32_t j = sorted_idx[p];
-                    w = weights[j];
-                    const float4 qj = quats[j];
+                    const float4 qj = sq[p];
                     const float qd = fabsf(__fmul_rn(8.0f, __fsub_rn(1.0f, dot4(q.x, q.y, q.z, q.w, qj.x, qj.y, qj.z, qj.w))));
                     if (qd < rot_thresh_sq) {
-                        tj = trans_in[j];
+                        const float4 tw = st[p];
+                        tj = make_float3(tw.x, tw.y, tw.z);
+                        w = tw.w;
                         pass = true;
                         if (!use_l1_norm) {
                             const float nd = norm3(__fsub_rn(tt.x, tj.x), __fsub_rn(tt.y, tj.y), __fsub_rn(tt.z, tj.z));
@@ -377,14 +392,15 @@ int cluster_run(const ModelTable &m, VoteResult &r, int shard, int n_shards) {
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, tb, (uint32_t *)nullptr, (uint32_t *)nullptr, (uint32_t *)nullptr,
                                     (uint32_t *)nullptr, K);
-    int rc = r.ws.reserve((size_t)K * (4 + 27 * 4 + 4 + 4 + 4 + sizeof(float3)) + 4 + tb);
+    int rc = r.ws.reserve((size_t)K * (4 + 27 * 4 + 4 + 4 + 4 + sizeof(float3) + 2 * sizeof(float4)) + 4 + tb + 1024);
     if (rc) return rc;
     uint32_t *cell = r.ws.take<uint32_t>(K), *adj = r.ws.take<uint32_t>((size_t)K * 27);
     uint32_t *iota = r.ws.take<uint32_t>(K), *shash = r.ws.take<uint32_t>(K), *sidx = r.ws.take<uint32_t>(K);
     float3 *tin = r.ws.take<float3>(K);
+    float4 *sq = r.ws.take<float4>(K), *st = r.ws.take<float4>(K);
     uint32_t *d_arg = r.ws.take<uint32_t>(1);
     void *tmp = r.ws.take_bytes(tb);
-    if (!cell || !adj || !iota || !shash || !sidx || !tin || !d_arg || !tmp) {
+    if (!cell || !adj || !iota || !shash || !sidx || !tin || !sq || !st || !d_arg || !tmp) {
         set_last_error("cluster: workspace too small");
         return PPF_ERR_CUDA;
     }
@@ -396,8 +412,10 @@ int cluster_run(const ModelTable &m, VoteResult &r, int shard, int n_shards) {
     // rot_clustering_kernel updates translations in place while neighbours read them (a race in the
     // reference when use_averaged_clusters is set); we read a snapshot instead, which is deterministic.
     PPF_CUDA_TRY(cudaMemcpyAsync(tin, r.trans, (size_t)K * sizeof(float3), cudaMemcpyDeviceToDevice, cur_stream()));
+    pose_gather_kernel<<<blocks_for(K), 256, 0, cur_stream()>>>(sidx, r.rots, tin, r.weighted, K, sq, st);
+    count_launch();
     const size_t mine = ((size_t)K + n_shards - 1) / n_shards;
-    cluster_kernel<<<(int)std::min<size_t>((mine * 32 + 255) / 256, 148 * 64), 256, 0, cur_stream()>>>(tin, r.rots, r.weighted, adj, shash, sidx, r.scores, r.trans, K,
+    cluster_kernel<<<(int)std::min<size_t>((mine * 32 + 255) / 256, 148 * 64), 256, 0, cur_stream()>>>(tin, r.rots, sq, st, adj, shash, r.scores, r.trans, K,
                                            m.d_dist, m.use_l1_norm, m.use_averaged_clusters, shard, n_shards);
     count_launch();
     PPF_CUDA_TRY(cudaGetLastError());
