@@ -472,17 +472,29 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
     // reference point with the most chunks left, repeats its hit collection (a few % of its work) and
     // draws chunks from the same counter, so the heaviest reference points do not leave the other SMs idle.
     uint32_t *const overflow = a.sched + 1 + a.ref_count;      // [0] = count, [1 ...] = jobs, [1 + R] = next to process
+    int c_lo = 0, c_hi = a.n_chunks;                           // SEGMENTS: the chunks of this job
     while (true) {
         __syncthreads();
         int job;
         if constexpr (SEGMENTS) {
+            // A job is (dense reference point, group of chunks).  Dense scenes register every reference point: one
+            // group = all chunks, so that a segment is collected once for all of them.  A sparse scene registers only a
+            // few outliers (configs[1] at ref_point_df = 1: a handful of points with more than 11k hits, 40 ms each on
+            // ONE SM while 147 idle): their chunks are spread over the idle CTAs, each repeating the collection.
+            const uint32_t n_dense = *(volatile uint32_t *)&overflow[0];
+            if (n_dense == 0u) break;
+            const uint32_t groups = min((uint32_t)a.n_chunks, max(1u, gridDim.x / n_dense));
             if (tid == 0) {
                 const uint32_t k = atomicAdd(&overflow[1 + a.ref_count], 1u);
-                s_job = k < *(volatile uint32_t *)&overflow[0] ? (int)overflow[1 + k] : -1;
+                s_job = k < n_dense * groups ? (int)overflow[1 + k / groups] : -1;
+                s_chunk = (int)(k % groups);
             }
             __syncthreads();
             job = s_job;
             if (job < 0) break;
+            const uint32_t g = (uint32_t)s_chunk;
+            c_lo = (int)(g * (uint32_t)a.n_chunks / groups);
+            c_hi = (int)((g + 1u) * (uint32_t)a.n_chunks / groups);
         } else {
         if (tid == 0) s_job = (int)atomicAdd(&a.sched[0], 1u);
         __syncthreads();
@@ -551,9 +563,9 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                 if (c >= a.n_chunks) break;
                 if (!sorted && n) { sort_and_cut(n); sorted = true; }
             } else {
-                if (c < 0 || c == a.n_chunks - 1) {
-                    if (c >= 0 && !more_segments) break;            // the last segment has met every chunk
-                    seg++; c = 0;
+                if (c < 0 || c == c_hi - 1) {
+                    if (c >= 0 && !more_segments) break;            // the last segment has met every chunk of the job
+                    seg++; c = c_lo;
                     __syncthreads();
                     if (tid == 0) s_nhits = 0;
                     __syncthreads();
@@ -573,7 +585,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                 } else {
                     c++;
                 }
-                if (seg > 0) {
+                if (seg > 0 && c_hi - c_lo > 1) {                   // (a single chunk stays in shared memory)
                     const uint32_t *src = a.acc_scratch + ((size_t)blockIdx.x * a.n_chunks + c) * ((size_t)kNAlphaBins * S);
                     for (int i = tid; i < kNAlphaBins * S; i += THREADS) acc[i] = src[i];
                 }
@@ -585,8 +597,10 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             __syncthreads();
             if constexpr (SEGMENTS) {
                 if (more_segments) {
-                    uint32_t *dst = a.acc_scratch + ((size_t)blockIdx.x * a.n_chunks + c) * ((size_t)kNAlphaBins * S);
-                    for (int i = tid; i < kNAlphaBins * S; i += THREADS) { dst[i] = acc[i]; acc[i] = 0; }
+                    if (c_hi - c_lo > 1) {
+                        uint32_t *dst = a.acc_scratch + ((size_t)blockIdx.x * a.n_chunks + c) * ((size_t)kNAlphaBins * S);
+                        for (int i = tid; i < kNAlphaBins * S; i += THREADS) { dst[i] = acc[i]; acc[i] = 0; }
+                    }
                     continue;
                 }
             }
