@@ -1,6 +1,7 @@
 """voxelGridDownsample (alignment.cpp:79-87) on the GPU: one centroid per occupied leaf, positions and
-(un-normalised) normals averaged, ascending leaf order (pcl::VoxelGrid semantics; PCL itself is absent, so
-parity is checked against the numpy restatement below, which is test infrastructure)."""
+(un-normalised) normals averaged, ascending leaf order (pcl::VoxelGrid semantics; PCL itself is absent from the image
+and from /root/reference, so the tests check it against a numpy restatement of the published filter that lives with
+the other test checkers (voxel_numpy in the repo's checker directory): PARITY UNPINNED)."""
 from __future__ import annotations
 
 import ctypes
@@ -32,26 +33,3 @@ def voxel_grid_downsample(points, normals, leaf: float):
         C.check(C.lib.ppf_voxel_grid(p.ctypes.data, 3, q.ctypes.data, 3, len(p), C.PPF_MEM_HOST, float(leaf),
                                      op.ctypes.data, oq.ctypes.data, ctypes.byref(n_out)))
     return op[: n_out.value].copy(), oq[: n_out.value].copy()
-
-
-def voxel_grid_downsample_numpy(points, normals, leaf: float):
-    """Restatement of pcl::VoxelGrid<PointNormal>::applyFilter (checker for the tests; float64 sums)."""
-    p = np.asarray(points, np.float32)
-    q = np.asarray(normals, np.float32)
-    ok = np.isfinite(p).all(1)
-    p, q = p[ok], q[ok]
-    if len(p) == 0:
-        return p, q
-    inv = np.float32(1.0) / np.float32(leaf)
-    ijk = np.floor(p * inv).astype(np.int64)
-    min_b = np.floor(p.min(0) * inv).astype(np.int64)
-    max_b = np.floor(p.max(0) * inv).astype(np.int64)
-    div = max_b - min_b + 1
-    cell = (ijk - min_b) @ np.array([1, div[0], div[0] * div[1]], np.int64)
-    order = np.argsort(cell, kind="stable")
-    cell_s = cell[order]
-    heads = np.flatnonzero(np.r_[True, cell_s[1:] != cell_s[:-1]])
-    counts = np.diff(np.r_[heads, len(cell_s)])
-    sp = np.add.reduceat(p[order].astype(np.float64), heads) / counts[:, None]
-    sq = np.add.reduceat(q[order].astype(np.float64), heads) / counts[:, None]
-    return sp.astype(np.float32), sq.astype(np.float32)

@@ -40,7 +40,7 @@ def test_pose_files_and_validation(tmp_path):
 
 
 def test_voxel_grid_numpy_restatement_properties():
-    from objective_slam_b200.voxel import voxel_grid_downsample_numpy
+    from oracle.voxel_numpy import voxel_grid_downsample_numpy
     p, n = synth.make_model(5000, seed=4)
     q, m = voxel_grid_downsample_numpy(p, n, 10.0)
     assert 50 < len(q) < 1200

@@ -8,7 +8,8 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("n,leaf", [(5000, 10.0), (200000, 2.5), (2, 0.5), (1000, 1000.0)])
 def test_voxel_grid_matches_restatement(n, leaf):
     from objective_slam_b200 import synth
-    from objective_slam_b200.voxel import voxel_grid_downsample, voxel_grid_downsample_numpy
+    from objective_slam_b200.voxel import voxel_grid_downsample
+    from oracle.voxel_numpy import voxel_grid_downsample_numpy
     p, q = synth.make_model(n, seed=n)
     q = q * np.random.default_rng(1).uniform(0.5, 1.0, (n, 1)).astype(np.float32)
     a, b = voxel_grid_downsample(p, q, leaf)
