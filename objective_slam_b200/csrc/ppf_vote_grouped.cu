@@ -65,6 +65,9 @@ bool vote_grouped_supported(const ModelTable &m, int ns) {
 
 // piece code: 0 = single hit (classical loop), c = 1..4 -> 2^(c+1) = 4 / 8 / 16 / 32 hits
 __device__ __forceinline__ uint32_t piece_hits(uint32_t code) { return code ? (2u << code) : 1u; }
+// guard band of the grouped loop, folded into the hit word (see vote2)
+constexpr uint32_t kGGuardShift = (kGuardLoA + (uint32_t)kNAngle - 1u) / (uint32_t)kNAngle;
+constexpr uint32_t kGGuardSpan  = 0u - (uint32_t)kNAngle * kGGuardShift - kGuardLoB;
 constexpr uint32_t kGSingleGrab = 4096;             // entries per ticket of a single hit (1024: 681 ms, 2048: 671, 4096: 667)
 __device__ __forceinline__ uint32_t piece_grab(uint32_t code) { return code ? (kGGrabVotes >> (code + 1)) : kGSingleGrab; }
 
@@ -119,9 +122,9 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
         for (uint32_t p = p0; p < p1; p++) {
             uint2 r = grp[p];
             r.x = 0u - r.x;                                    // staged negated
-            uint32_t bin;
-            const uint32_t margin = alpha_bin_margin(hit_ones, r.x, bin);
-            if (r.y != trash && (margin >= kGuardSpan || (r.x & kSlowBit) || hit_slow)) {
+            const unsigned long long pr = (unsigned long long)(hit_ones - kGGuardShift - r.x) * (unsigned long long)kNAngle;
+            const uint32_t bin = (uint32_t)(pr >> 32), margin = (uint32_t)pr;     // the cell the loop incremented
+            if (r.y != trash && (margin >= kGGuardSpan || (r.x & kSlowBit) || hit_slow)) {
                 const uint32_t j = (p & 1u) * 32u + (p >> 1) * EG + g;          // entry index within the block
                 atomicSub(&ctx.acc[bin * (uint32_t)ctx.stride + (r.x & kLocMask)], 1u);
                 exact_vote(ctx, FS, s_i, r.x, blk_pos + j);
@@ -134,17 +137,18 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
     // IMAD.IADD, i.e. a third op per vote (with the IMAD.WIDE and the address IMAD) on the FMA-heavy pipe, which ncu
     // shows 68% busy over the whole kernel (math-pipe throttle the #3 stall reason) against 36% for the ALU pipe.
     const uint32_t zero = ctx.opaque_zero;
+    // The guard-band test costs half an instruction per vote: the hit word is lowered by a = ceil(kGuardLoA / 30), so
+    // that the low word of 30 (hit - a - entry) IS the margin (low word - kGuardLoA, up to < 30 units of slack on the
+    // safe side) and two margins are max-reduced by one VIMNMX3.  A vote whose low word was below 30 a lands one bin
+    // lower (or in bin 29 after a wrap): always a valid cell, and exactly the votes the repair moves anyway -- the
+    // repair recomputes the same shifted product to find the cell it has to decrement.
+    const uint32_t hit_g = hit_ones - kGGuardShift;
     auto vote2 = [&](const uint4 q, uint32_t &worst) {
-        {
-            const unsigned long long p = (unsigned long long)max(hit_ones + q.x, zero) * (unsigned long long)kNAngle;
-            worst = max(worst, (uint32_t)p - kGuardLoA);
-            red_shared_inc((uint32_t)(p >> 32) * S4 + q.y);
-        }
-        {
-            const unsigned long long p = (unsigned long long)max(hit_ones + q.z, zero) * (unsigned long long)kNAngle;
-            worst = max(worst, (uint32_t)p - kGuardLoA);
-            red_shared_inc((uint32_t)(p >> 32) * S4 + q.w);
-        }
+        const unsigned long long pa = (unsigned long long)max(hit_g + q.x, zero) * (unsigned long long)kNAngle;
+        const unsigned long long pb = (unsigned long long)max(hit_g + q.z, zero) * (unsigned long long)kNAngle;
+        red_shared_inc((uint32_t)(pa >> 32) * S4 + q.y);
+        red_shared_inc((uint32_t)(pb >> 32) * S4 + q.w);
+        worst = max(worst, max((uint32_t)pa, (uint32_t)pb));
     };
 
     // the entries of the next two blocks are in flight while a block votes
@@ -181,7 +185,7 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
                 const uint4 q0 = src[0], q1 = src[1], q2 = src[2], q3 = src[3];
                 uint32_t worst = worst0;
                 vote2(q0, worst); vote2(q1, worst); vote2(q2, worst); vote2(q3, worst);
-                if (worst >= kGuardSpan) repair(0, 8, pos_grab + blk0);
+                if (worst >= kGGuardSpan) repair(0, 8, pos_grab + blk0);
                 p = 8;
             }
 #pragma unroll 1
@@ -190,13 +194,13 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
                     const uint4 q0 = src[p / 2], q1 = src[p / 2 + 1], q2 = src[p / 2 + 2], q3 = src[p / 2 + 3];
                     uint32_t worst = worst0;
                     vote2(q0, worst); vote2(q1, worst); vote2(q2, worst); vote2(q3, worst);
-                    if (worst >= kGuardSpan) repair(p, p + 8, pos_grab + blk0);
+                    if (worst >= kGGuardSpan) repair(p, p + 8, pos_grab + blk0);
                 }
                 {
                     const uint4 q0 = src[p / 2 + 4], q1 = src[p / 2 + 5], q2 = src[p / 2 + 6], q3 = src[p / 2 + 7];
                     uint32_t worst = worst0;
                     vote2(q0, worst); vote2(q1, worst); vote2(q2, worst); vote2(q3, worst);
-                    if (worst >= kGuardSpan) repair(p + 8, p + 16, pos_grab + blk0);
+                    if (worst >= kGGuardSpan) repair(p + 8, p + 16, pos_grab + blk0);
                 }
             }
         } else {
@@ -208,17 +212,17 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
             for (uint32_t k = 0; k < pairs; k++) {
                 const uint4 q = src[k];
                 {
-                    const unsigned long long p = (unsigned long long)(hit_ones + q.x) * (unsigned long long)kNAngle;
-                    if (q.y != trash) worst = max(worst, (uint32_t)p - kGuardLoA);
+                    const unsigned long long p = (unsigned long long)(hit_g + q.x) * (unsigned long long)kNAngle;
+                    if (q.y != trash) worst = max(worst, (uint32_t)p);
                     red_shared_inc((uint32_t)(p >> 32) * S4 + q.y);
                 }
                 {
-                    const unsigned long long p = (unsigned long long)(hit_ones + q.z) * (unsigned long long)kNAngle;
-                    if (q.w != trash) worst = max(worst, (uint32_t)p - kGuardLoA);
+                    const unsigned long long p = (unsigned long long)(hit_g + q.z) * (unsigned long long)kNAngle;
+                    if (q.w != trash) worst = max(worst, (uint32_t)p);
                     red_shared_inc((uint32_t)(p >> 32) * S4 + q.w);
                 }
             }
-            if (worst >= kGuardSpan) repair(0, 2u * pairs, pos_grab + blk0);
+            if (worst >= kGGuardSpan) repair(0, 2u * pairs, pos_grab + blk0);
         }
         c0 = n0; c1 = n1; n0 = m0; n1 = m1;
     }
