@@ -359,9 +359,9 @@ int features_tile(const Cloud &c, float d_dist, unsigned df, int rb, int re, int
 //   2. cell_keys_kernel: FNV key of every occupied cell (a few thousand hashes); sort + unique of those keys ->
 //      hashkeys[U] (cells whose keys collide share a bucket, as in the reference, where only the key is compared);
 //      cell_table_kernel: cell -> bucket rank;
-//   3. pair_ranks_kernel: code -> rank in place (one L2-resident table read);                   4 B read, 4 B written
-//      own stable LSD radix sort (ppf_radix.cuh) over ceil(log2 U) rank bits (13 for a 10k-point model: 2 passes
-//      instead of 4 over 32 key bits), the pair index as implicit payload of pass 0;    per pass 4 + 8 B read, 8 B written
+//   3. own stable LSD radix sort (ppf_radix.cuh) over ceil(log2 U) rank bits (13 for a 10k-point model: 2 passes
+//      instead of 4 over 32 key bits); the histogram kernel of the first pass turns the codes into ranks in place (one
+//      L2-resident table read) and the pair index is the implicit payload of that pass;  per pass 4 + 8 B read, 8 B written
 //   4. bucket_bounds_kernel: first / counts from the rank boundaries of the sorted run.         4 B / pair read
 // The arrays are bit-identical to the reference's: ranks ascend with the keys and the sort is stable in the pair index.
 constexpr uint32_t kKey0Cell = 0xFFFFFFFFu;           // cell code of a pair whose key is 0 (self pair, NaN distance)
@@ -774,13 +774,11 @@ int model_build(ModelTable &m) {
         count_launch();
         PPF_CUDA_TRY(cub::DeviceRadixSort::SortPairs(tmp, sort_tmp, ranks, ranks_sorted, iota, m.map, total, 0, rank_bits, cur_stream()));
     } else {
-        // codes -> ranks in place; pass 0 takes the pair index as the payload, so no index array is written before the
-        // sort.  (Reading the codes THROUGH the cell table inside pass 0 was measured slower: the dependent gather
-        // sits on the critical path of a tile, 2.04 ms against 0.22 + 1.0 ms.)
+        // the histogram kernel of pass 0 turns the codes into ranks in place (cell table read) and pass 0 takes the pair
+        // index as the payload: no rank pass, no index array.  (Translating inside the SCATTER kernel was measured
+        // slower: there the dependent gather sits on the critical path of a tile, 2.04 ms.)
         if (plan.scratch_words * 4 > sort_tmp) { set_last_error("model: scratch arena too small"); return PPF_ERR_CUDA; }
-        pair_ranks_kernel<<<grid, 256, 0, cur_stream()>>>(ranks, m.cell2bucket, total, nullptr);
-        count_launch();
-        count_launch(radix_sort_pairs(rk, pv, total, plan, (uint32_t *)tmp, cur_stream(), nullptr, true));
+        count_launch(radix_sort_pairs(rk, pv, total, plan, (uint32_t *)tmp, cur_stream(), m.cell2bucket, true));
         ranks_final = rk[plan.passes & 1];
     }
     PPF_CUDA_TRY(cudaGetLastError());

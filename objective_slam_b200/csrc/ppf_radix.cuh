@@ -4,11 +4,11 @@
 // bits = 2 passes of 7 / 6 bits over 8-byte records.
 //
 // One pass = three launches:
-//   radix_hist_kernel     per tile of 8192 records: digit histogram (shared-memory atomics) -> tilehist[digit][tile]
+//   radix_hist_kernel     per tile of 4096 records: digit histogram (shared-memory atomics) -> tilehist[digit][tile]
 //   scan (3 small kernels) exclusive prefix over tilehist in (digit, tile) order = where the tile's records of a digit go
 //   radix_scatter_kernel  per tile: every warp ranks the records of its slice among those of the same digit, in index
-//                          order (match.any groups the lanes of a digit; the group's leader advances the warp's
-//                          count), a block scan turns the counts into offsets, the records go to a shared-memory
+//                          order (the lanes of a digit are grouped by ballots in the first pass, by match.any later;
+//                          the group's leader advances the warp's count), a block scan turns the counts into offsets, the records go to a shared-memory
 //                          staging area sorted by digit and leave it in coalesced runs.  Stable: a warp owns a
 //                          contiguous slice of the tile; warps and tiles are ordered by the prefix sums.
 // HBM traffic per pass and record: 4 B (histogram) + 8 B read + 8 B written.
@@ -19,9 +19,9 @@
 
 namespace ppf {
 
-// Pass 0 may translate what it reads through a table (the model build sorts by bucket rank but has cell codes in
-// memory: rank = lut[code], code 0xFFFFFFFF and table value 0xFFFFFFFF -> rank 0) and may take the record's index as
-// its value (vals_in == nullptr): neither the ranks nor an iota array are then ever written.
+// The histogram kernel of pass 0 may translate the keys through a table, in place (the model build sorts by bucket rank
+// but has cell codes in memory: rank = lut[code], code 0xFFFFFFFF and table value 0xFFFFFFFF -> rank 0), and pass 0
+// may take the record's index as its value (vals_in == nullptr): no separate rank pass, no iota array.
 __device__ __forceinline__ uint32_t rx_key(const uint32_t *__restrict__ keys, size_t p, const uint32_t *__restrict__ lut) {
     const uint32_t c = keys[p];
     if (!lut) return c;
@@ -30,12 +30,14 @@ __device__ __forceinline__ uint32_t rx_key(const uint32_t *__restrict__ keys, si
 }
 
 constexpr int kRxThreads = 512;
-constexpr int kRxItems   = 16;
-constexpr int kRxTile    = kRxThreads * kRxItems;      // 8192 records per CTA
+constexpr int kRxItems   = 8;
+constexpr int kRxTile    = kRxThreads * kRxItems;      // 4096 records per CTA
 constexpr int kRxMaxBins = 256;
 constexpr int kRxWarps   = kRxThreads / 32;
 
-__global__ void __launch_bounds__(kRxThreads) radix_hist_kernel(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ lut,
+// translate != nullptr: the keys are read through the table and WRITTEN BACK translated (the first pass of the model
+// build turns cell codes into bucket ranks on the way: no separate rank pass)
+__global__ void __launch_bounds__(kRxThreads) radix_hist_kernel(uint32_t *keys, const uint32_t *__restrict__ translate,
                                                                 size_t n, int shift, uint32_t mask, uint32_t ntiles,
                                                                 uint32_t *tilehist) {
     __shared__ uint32_t hist[kRxMaxBins];
@@ -46,7 +48,11 @@ __global__ void __launch_bounds__(kRxThreads) radix_hist_kernel(const uint32_t *
 #pragma unroll
         for (int j = 0; j < kRxItems; j++) {
             const size_t p = base + (size_t)j * kRxThreads + threadIdx.x;
-            if (p < n) atomicAdd(&hist[(rx_key(keys, p, lut) >> shift) & mask], 1u);
+            if (p < n) {
+                const uint32_t k = rx_key(keys, p, translate);
+                if (translate) keys[p] = k;
+                atomicAdd(&hist[(k >> shift) & mask], 1u);
+            }
         }
         __syncthreads();
         for (int i = threadIdx.x; i <= (int)mask; i += kRxThreads) tilehist[(size_t)i * ntiles + tile] = hist[i];
@@ -119,7 +125,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_apply_kernel(uint32_t *a, s
 }
 
 // ---- scatter ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kRxThreads) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
+template <bool USE_MATCH>
+__global__ void __launch_bounds__(kRxThreads, 2) radix_scatter_kernel(const uint32_t *__restrict__ keys_in,
                                                                    const uint32_t *__restrict__ lut,
                                                                    const uint32_t *__restrict__ vals_in, size_t n, int shift,
                                                                    uint32_t mask, uint32_t ntiles,
@@ -135,6 +142,7 @@ __global__ void __launch_bounds__(kRxThreads) radix_scatter_kernel(const uint32_
     __shared__ uint32_t ws[32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
+    const int nbits = 32 - __clz((int)mask);                        // digit bits of this pass (mask = 2^nbits - 1)
     for (uint32_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const size_t base = (size_t)tile * kRxTile + (size_t)warp * (kRxItems * 32) + lane;      // warp-blocked slices
         uint32_t k[kRxItems], v[kRxItems], lpos[kRxItems];
@@ -153,7 +161,21 @@ __global__ void __launch_bounds__(kRxThreads) radix_scatter_kernel(const uint32_
         for (int j = 0; j < kRxItems; j++) {
             const size_t p = base + (size_t)j * 32;
             const uint32_t d = p < n ? ((k[j] >> shift) & mask) : mask + 1u;
-            const unsigned peers = __match_any_sync(0xffffffffu, d);
+            // Lanes with the same digit.  match.any takes time proportional to the number of DISTINCT values in the warp:
+            // fine once the records arrive sorted by the lower digits (few distinct higher digits per warp: 527 us for
+            // the second pass of a 10k-point model against 726 us with ballots), slow on the first pass, where the
+            // records come in pair order (~28 distinct digits per warp: 949 us against 781 us) -- there the lanes are
+            // grouped by one ballot per digit bit (+ the bit of the past-the-end bin), a fixed cost.
+            unsigned peers = 0xffffffffu;
+            if constexpr (USE_MATCH) {
+                peers = __match_any_sync(0xffffffffu, d);
+            } else {
+                for (int b = 0; b <= nbits; b++) {
+                    const bool bit = (d >> b) & 1u;
+                    const unsigned bal = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? bal : ~bal;
+                }
+            }
             const int leader = __ffs((int)peers) - 1;
             uint32_t old = 0;
             if (lane == leader) { old = mine[d]; mine[d] = old + (uint32_t)__popc(peers); }
@@ -253,16 +275,22 @@ inline int radix_sort_pairs(uint32_t *keys[2], uint32_t *vals[2], size_t n, cons
         uint32_t *bsum = scratch + (size_t)kRxMaxBins * pl.ntiles;
         const uint32_t nblk = (uint32_t)((hist_n + kScanBlock - 1) / kScanBlock);
         const unsigned grid = pl.ntiles < 148u * 8u ? pl.ntiles : 148u * 8u;
-        const uint32_t *lut0 = pass == 0 ? lut : nullptr;
+        const uint32_t *lut0 = nullptr;                  // (the histogram kernel of pass 0 has translated the keys in place)
         const uint32_t *vin = (pass == 0 && index_values) ? nullptr : vals[cur];
-        radix_hist_kernel<<<grid, kRxThreads, 0, stream>>>(keys[cur], lut0, n, shift, mask, pl.ntiles, tilehist);
+        radix_hist_kernel<<<grid, kRxThreads, 0, stream>>>(keys[cur], pass == 0 ? lut : nullptr, n, shift, mask, pl.ntiles, tilehist);
         scan_block_sums_kernel<<<nblk, kScanThreads, 0, stream>>>(tilehist, hist_n, bsum);
         scan_sums_kernel<<<1, kScanThreads, 0, stream>>>(bsum, nblk);
         scan_apply_kernel<<<nblk, kScanThreads, 0, stream>>>(tilehist, hist_n, bsum);
         const size_t smem = ((size_t)(kRxWarps + 2) * (mask + 2u) + 2u * kRxTile) * sizeof(uint32_t);
-        cudaFuncSetAttribute(radix_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        radix_scatter_kernel<<<grid, kRxThreads, smem, stream>>>(keys[cur], lut0, vin, n, shift, mask, pl.ntiles, tilehist,
-                                                                 keys[cur ^ 1], vals[cur ^ 1]);
+        if (pass == 0) {
+            cudaFuncSetAttribute(radix_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            radix_scatter_kernel<false><<<grid, kRxThreads, smem, stream>>>(keys[cur], lut0, vin, n, shift, mask, pl.ntiles,
+                                                                            tilehist, keys[cur ^ 1], vals[cur ^ 1]);
+        } else {
+            cudaFuncSetAttribute(radix_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            radix_scatter_kernel<true><<<grid, kRxThreads, smem, stream>>>(keys[cur], lut0, vin, n, shift, mask, pl.ntiles,
+                                                                           tilehist, keys[cur ^ 1], vals[cur ^ 1]);
+        }
         launches += 5;
         shift += pl.pass_bits[pass];
         cur ^= 1;
