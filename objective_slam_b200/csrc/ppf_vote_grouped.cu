@@ -69,7 +69,11 @@ __device__ __forceinline__ uint32_t piece_hits(uint32_t code) { return code ? (2
 constexpr uint32_t kGGuardShift = (kGuardLoA + (uint32_t)kNAngle - 1u) / (uint32_t)kNAngle;
 constexpr uint32_t kGGuardSpan  = 0u - (uint32_t)kNAngle * kGGuardShift - kGuardLoB;
 constexpr uint32_t kGSingleGrab = 4096;             // entries per ticket of a single hit (1024: 681 ms, 2048: 671, 4096: 667)
-__device__ __forceinline__ uint32_t piece_grab(uint32_t code) { return code ? (kGGrabVotes >> (code + 1)) : kGSingleGrab; }
+constexpr uint32_t kGRestCode  = 5;                 // piece code: the 3..31 hits a bucket has beyond its pieces of 32 (vote_rest)
+constexpr uint32_t kGRestGrab  = 4096;              // entries per ticket of such a piece
+__device__ __forceinline__ uint32_t piece_grab(uint32_t code) {
+    return code == kGRestCode ? kGRestGrab : code ? (kGGrabVotes >> (code + 1)) : kGSingleGrab;
+}
 
 struct GroupCtx {
     const unsigned long long *queue;
@@ -88,6 +92,9 @@ struct GroupCtx {
 __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx &gc, const FrameYZ &FS, uint32_t i0,
                                              uint32_t code, const uint32_t *__restrict__ entries, uint32_t pos_grab,
                                              uint32_t ngrab, int lane, uint32_t &n_exact) {
+    // (pieces of 4 / 8 / 16 hits are no longer cut: the hits a bucket has beyond its pieces of 32 go through vote_rest.
+    // HG stays a run-time value all the same: with lhg = 5 as a constant ptxas unrolls the 64-position loop fully and
+    // the kernel slows from 591 to 628 ms on configs[1] -- instruction cache.)
     const uint32_t lhg = code + 1u;                 // log2(HG)
     const uint32_t HG = 1u << lhg, EG = 32u >> lhg, K = 2u * HG;
     const uint32_t g = (uint32_t)lane >> lhg;
@@ -225,6 +232,94 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
             if (worst >= kGGuardSpan) repair(0, 2u * pairs, pos_grab + blk0);
         }
         c0 = n0; c1 = n1; n0 = m0; n1 = m1;
+    }
+}
+
+// The r = 3..31 hits a bucket has beyond its pieces of 32, against entries [pos_grab, pos_grab + ngrab): lane = ENTRY.
+// A warp holds 32 x kRestE pre-decoded entries (negated entry word, accumulator row address) in registers and loops
+// over the r hits; a hit record is warp-uniform and comes from the sorted queue with one broadcast LDS.64.  No staging,
+// no STS, and ONE pass over the entries for any r -- the staged loop needs a power-of-two piece (16 / 8 / 4 hits, then
+// single hits through the one-hit loop) and re-stages the entries for each: 3 passes for r = 13.  The lanes of an
+// ATOMS are 32 adjacent entries here (random bins: ~1.8 wavefronts against 1.1 in the staged loop, where 32 hits share
+// an entry), which is why pieces of 32 keep the staged loop (tools/microbench: 14.2 votes/clk/SM staged at 32 hits
+// against 10.9 here; 9.9 / 7.9 here at 8 / 4 hits against 9.2 / ~6 staged, before the staging cost).
+#ifndef PPF_REST_E
+#define PPF_REST_E 8
+#endif
+#ifndef PPF_REST_MIN
+#define PPF_REST_MIN 3
+#endif
+#ifndef PPF_REST_UNROLL
+#define PPF_REST_UNROLL 1
+#endif
+constexpr int kRestE = PPF_REST_E;
+constexpr int kRestUnroll = PPF_REST_UNROLL;
+__device__ __forceinline__ void vote_rest(const VoteCtx &ctx, const GroupCtx &gc, const FrameYZ &FS, uint32_t i0, uint32_t r,
+                                          const uint32_t *__restrict__ entries, uint32_t pos_grab, uint32_t ngrab, int lane,
+                                          uint32_t &n_exact) {
+    const uint32_t S4 = (uint32_t)ctx.stride * 4u;
+    uint32_t trash = gc.trash_addr, acc_base = ctx.acc_addr;
+    asm volatile("" : "+r"(trash), "+r"(acc_base));
+    const uint32_t zero = ctx.opaque_zero;
+    const unsigned long long *hits = gc.queue + i0;
+    const uint32_t nblocks = (ngrab + 32u * kRestE - 1u) / (32u * kRestE);
+    uint32_t raw[kRestE];
+#pragma unroll
+    for (int u = 0; u < kRestE; u++) {
+        const uint32_t j = (uint32_t)u * 32u + (uint32_t)lane;
+        raw[u] = j < ngrab ? __ldg(entries + pos_grab + j) : 0u;
+    }
+#pragma unroll 1
+    for (uint32_t blk = 0; blk < nblocks; blk++) {
+        const uint32_t blk0 = blk * 32u * kRestE;
+        uint32_t neg[kRestE], adr[kRestE], slow_any = 0;
+#pragma unroll
+        for (int u = 0; u < kRestE; u++) {
+            const uint32_t j = blk0 + (uint32_t)u * 32u + (uint32_t)lane;
+            const bool valid = j < ngrab;
+            neg[u] = valid ? 0u - raw[u] : 0u;
+            adr[u] = valid ? acc_base + (raw[u] & kLocMask) * 4u : trash;
+            slow_any |= valid ? raw[u] : 0u;
+        }
+        // the entries of the next block are in flight while this one votes
+#pragma unroll
+        for (int u = 0; u < kRestE; u++) {
+            const uint32_t j = blk0 + 32u * kRestE + (uint32_t)u * 32u + (uint32_t)lane;
+            raw[u] = j < ngrab ? __ldg(entries + pos_grab + j) : 0u;
+        }
+        const uint32_t worst0 = (slow_any & kSlowBit) ? 0xFFFFFFFFu : 0u;
+#pragma unroll kRestUnroll
+        for (uint32_t h = 0; h < r; h++) {
+            const unsigned long long rec = hits[h];
+            const uint32_t hit_ones = ((uint32_t)(rec >> kGThetaShift) << kThetaShift) | kLowOnes;
+            const uint32_t hit_g = hit_ones - kGGuardShift;
+            uint32_t worst = (((uint32_t)rec >> 23) & 1u) ? 0xFFFFFFFFu : worst0;
+#pragma unroll
+            for (int u = 0; u < kRestE; u += 2) {
+                const unsigned long long pa = (unsigned long long)max(hit_g + neg[u], zero) * (unsigned long long)kNAngle;
+                const unsigned long long pb = (unsigned long long)max(hit_g + neg[u + 1], zero) * (unsigned long long)kNAngle;
+                red_shared_inc((uint32_t)(pa >> 32) * S4 + adr[u]);
+                red_shared_inc((uint32_t)(pb >> 32) * S4 + adr[u + 1]);
+                worst = max(worst, max((uint32_t)pa, (uint32_t)pb));
+            }
+            if (worst >= kGGuardSpan) {
+                // some vote of this hit is not provably in its fast bin (or the hit / an entry is flagged slow): move
+                // those from the cell the loop incremented to the exact one
+                const bool hit_slow = ((uint32_t)rec >> 23) & 1u;
+                const uint32_t s_i = (uint32_t)rec & kGIndexMask;
+#pragma unroll
+                for (int u = 0; u < kRestE; u++) {
+                    if (adr[u] == trash) continue;
+                    const uint32_t e = 0u - neg[u];
+                    const unsigned long long pr = (unsigned long long)(hit_g - e) * (unsigned long long)kNAngle;
+                    if ((uint32_t)pr >= kGGuardSpan || (e & kSlowBit) || hit_slow) {
+                        atomicSub(&ctx.acc[(uint32_t)(pr >> 32) * (uint32_t)ctx.stride + (e & kLocMask)], 1u);
+                        exact_vote(ctx, FS, s_i, e, pos_grab + blk0 + (uint32_t)u * 32u + (uint32_t)lane);
+                        n_exact++;
+                    }
+                }
+            }
+        }
     }
 }
 
@@ -382,12 +477,10 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             uint32_t hc = 0;                                       // head << 3 | code
             if (o < full) { if ((o & 31u) == 0u) hc = 8u | 4u; }
             else {
+                // the rest: 3..31 hits as ONE piece (vote_rest, one pass over the entries), 1 or 2 as single hits
                 const uint32_t r = h - full, q = o - full;
-                const uint32_t p16 = r & 16u, p8 = r & 8u, p4 = r & 4u;
-                if (p16 && q == 0u) hc = 8u | 3u;
-                else if (p8 && q == p16) hc = 8u | 2u;
-                else if (p4 && q == p16 + p8) hc = 8u | 1u;
-                else if (q >= p16 + p8 + p4) hc = 8u;
+                if (r >= (uint32_t)PPF_REST_MIN) { if (q == 0u) hc = 8u | kGRestCode; }
+                else hc = 8u;
             }
             heads |= (unsigned long long)hc << (4 * k);
         }
@@ -449,8 +542,18 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
             const uint2 rg = __ldg(ranges + (uint32_t)(rec >> kGBucketShift));
             const uint32_t off = (t - gstart) * piece_grab(code);
             const uint32_t ngrab = min(piece_grab(code), rg.y - off);
-            if (lane == 0) my_votes += (unsigned long long)ngrab * piece_hits(code);
             const uint32_t pos_grab = rg.x + off;
+            if (code == kGRestCode) {
+                // hits of this piece: the records from i0 to the end of the bucket's group (at most 31)
+                const unsigned long long key = rec >> kGBucketShift;
+                const uint32_t idx = i0 + (uint32_t)lane;
+                const unsigned same = __ballot_sync(0xffffffffu, idx < n && (queue[idx] >> kGBucketShift) == key);
+                const uint32_t r = (uint32_t)__popc(same);
+                if (lane == 0) my_votes += (unsigned long long)ngrab * r;
+                vote_rest(ctx, gc, FS, i0, r, a.entries, pos_grab, ngrab, lane, my_exact);
+                continue;
+            }
+            if (lane == 0) my_votes += (unsigned long long)ngrab * piece_hits(code);
             if (code == 0u) {
                 const uint32_t hit_word = ((uint32_t)(rec >> kGThetaShift) << kThetaShift) |
                                           ((((uint32_t)rec >> 23) & 1u) << kLocBits);
