@@ -261,7 +261,8 @@ int ppf_registration_sharded(const ppf_cloud_t *scene_clouds, int num_scenes, co
 /* ppf_registration (ppf.h:9-15): for every scene i and model j build Scene(scene_i, d_dist_j,
  * df) and Model(model_j, d_dist_j, ...), run ppf_lookup and write the best model->scene pose to
  * poses_out[(i*num_models + j)*16 ..] (row-major 4x4).  Host clouds in, host poses out.
- * cpu_clustering selects the PCL-style greedy clustering (transformation_clustering.cpp:62-137).
+ * cpu_clustering selects the PCL-style greedy clustering (transformation_clustering.cpp:62-137; Eigen's conversions
+ * are restated, not linked: PARITY UNPINNED for that option).
  * device follows the reference: the device used is min(device_count-1, device) (ppf.cu:45);
  * model_weights is accepted and ignored, as in the reference (ppf.cu:35). status_out (optional,
  * num_scenes*num_models) receives the per-pair status (PPF_ERR_NO_VOTES leaves a zero pose). */

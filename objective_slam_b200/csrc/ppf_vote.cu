@@ -386,6 +386,9 @@ int vote_run(const ModelTable &m, const Cloud &scene, unsigned df, int shard_ran
         a.d_dist = m.d_dist; a.inv_d = m.inv_d_dist; a.K_d = m.K_d; a.U = m.U;
         a.cell2bucket = m.cell2bucket; a.ranges = m.ranges; a.entries = m.entries; a.map = m.map;
         a.n_chunks = m.n_chunks; a.chunk_rows = m.chunk_rows;
+        // average entries per (bucket, chunk): >= 512 -> long slices.  PPF_B200_REST_E=4|8 forces it (A/B hook)
+        a.rest_long = (double)m.cloud.n * m.cloud.n / std::max(1u, m.U) / std::max(1, m.n_chunks) >= 512.0;
+        if (const char *e = getenv("PPF_B200_REST_E")) a.rest_long = atoi(e) >= 8;
         a.queue_cap = 0; a.sched = nullptr; a.acc_scratch = nullptr; a.opaque_zero = 0;
         a.replay = nullptr; a.replay_cap = 0;
         a.thr = m.vote_count_threshold; a.emit_all = emit_all;

@@ -31,6 +31,7 @@ struct VoteArgs {
     // grouped kernel only: hit queue capacity (records); work counters: sched[0] = next reference point,
     // sched[1 + r] = next chunk of reference point r (zeroed before the launch)
     int queue_cap;
+    int rest_long;                                // grouped kernel: bucket slices are long (8 entries per lane in vote_rest, else 4)
     uint32_t opaque_zero;                         // always 0; a third add operand the compilers cannot fold (see vote_grouped)
     uint32_t *sched;
     uint32_t *acc_scratch;                        // [CTAs][n_chunks][31 x S]: accumulators parked between scene segments

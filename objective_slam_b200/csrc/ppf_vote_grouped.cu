@@ -243,17 +243,17 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
 // ATOMS are 32 adjacent entries here (random bins: ~1.8 wavefronts against 1.1 in the staged loop, where 32 hits share
 // an entry), which is why pieces of 32 keep the staged loop (tools/microbench: 14.2 votes/clk/SM staged at 32 hits
 // against 10.9 here; 9.9 / 7.9 here at 8 / 4 hits against 9.2 / ~6 staged, before the staging cost).
-#ifndef PPF_REST_E
-#define PPF_REST_E 8
-#endif
 #ifndef PPF_REST_MIN
 #define PPF_REST_MIN 3
 #endif
 #ifndef PPF_REST_UNROLL
 #define PPF_REST_UNROLL 1
 #endif
-constexpr int kRestE = PPF_REST_E;
 constexpr int kRestUnroll = PPF_REST_UNROLL;
+// kRestE entries per lane: 8 for tables with long bucket slices, 4 for short ones (a block of 32 x 8 slots would be
+// mostly empty there: the 20 x 2k-point models of configs[3] leave ~200 entries per bucket and chunk, 14.5 s per scene
+// with 8 against 11.8 s with 4; the 10k-point model of configs[1] ~1,150: 574 ms with 8 against 620 with 4)
+template <int kRestE>
 __device__ __forceinline__ void vote_rest(const VoteCtx &ctx, const GroupCtx &gc, const FrameYZ &FS, uint32_t i0, uint32_t r,
                                           const uint32_t *__restrict__ entries, uint32_t pos_grab, uint32_t ngrab, int lane,
                                           uint32_t &n_exact) {
@@ -359,7 +359,7 @@ __device__ __forceinline__ uint32_t queue_lower_bound(const unsigned long long *
 // chunk waiting in global scratch between two segments (60 KB per chunk and segment each way: noise next to
 // the votes).  Two instantiations keep the segment bookkeeping out of the normal kernel's registers
 // (one kernel with both paths: 104 bytes of spills, -6% on configs[1]).
-template <int THREADS, bool SEGMENTS>
+template <int THREADS, bool SEGMENTS, int REST_E>
 __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int C = a.chunk_rows, S = acc_stride(C);
@@ -551,7 +551,7 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
                 const unsigned same = __ballot_sync(0xffffffffu, idx < n && (queue[idx] >> kGBucketShift) == key);
                 const uint32_t r = (uint32_t)__popc(same);
                 if (lane == 0) my_votes += (unsigned long long)ngrab * r;
-                vote_rest(ctx, gc, FS, i0, r, a.entries, pos_grab, ngrab, lane, my_exact);
+                vote_rest<REST_E>(ctx, gc, FS, i0, r, a.entries, pos_grab, ngrab, lane, my_exact);
                 continue;
             }
             if (lane == 0) my_votes += (unsigned long long)ngrab * piece_hits(code);
@@ -801,11 +801,20 @@ int vote_grouped_launch(VoteArgs a, int ref_count) {
     // work from the counters in a.sched (zeroed by the caller)
     const long long grid = vote_grouped_ctas();
     const size_t smem = vote_grouped_smem(a.chunk_rows);
-    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    vote_kernel_grouped<kGThreads, false><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
-    // reference points whose hits did not fit the queue (none on sparse scenes: the kernel then exits at once)
-    vote_kernel_grouped<kGThreads, true><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
+    // entries per lane of vote_rest by the average bucket slice per chunk (see vote_rest)
+    const bool long_slices = a.rest_long != 0;
+    if (long_slices) {
+        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vote_kernel_grouped<kGThreads, false, 8><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
+        // reference points whose hits did not fit the queue (none on sparse scenes: the kernel then exits at once)
+        vote_kernel_grouped<kGThreads, true, 8><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
+    } else {
+        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vote_kernel_grouped<kGThreads, false, 4><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
+        vote_kernel_grouped<kGThreads, true, 4><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
+    }
     count_launch(2);
     return PPF_OK;
 }

@@ -240,6 +240,27 @@ def test_config3_model_build_stress_5k():
     assert len(t[3]) == 25_000_000 and t[1][0] == 5000          # bucket 0 = the self pairs
 
 
+@pytest.mark.parametrize("sort", ["own", "cub"])
+@pytest.mark.parametrize("nm,tau", [(1200, 0.004), (700, 0.02), (90, 0.3)])
+def test_model_table_radix_passes(monkeypatch, vote_kernel, sort, nm, tau):
+    """model_description with few / many buckets: the table is sorted by bucket rank over ceil(log2 U) bits, i.e. one,
+    two or three passes of the repo's radix sort (tau_d = 0.004: ~1e5 buckets, 17-18 rank bits, odd pass count, the
+    payload ping-pong ends in the map either way), and the same with the library sort behind the A/B hook.
+    hashkeys / counts / firstHashkeyIndex / hashkeyToDataMap equal the reference's ParallelHashArray."""
+    if vote_kernel != "grouped":
+        pytest.skip("the table build does not depend on the vote kernel")
+    import objective_slam_b200 as ppf
+    from oracle import refgpu
+    monkeypatch.setenv("PPF_B200_SORT", sort)
+    mp, mn, _, _, d, _ = clouds(nm, 10, tau, seed=61 + nm)
+    rt = refgpu.RefModel(mp, mn, d).table()
+    t = ppf.Model(mp, mn, d).table()
+    for name, a, b in zip(("hashkeys", "counts", "first", "map"), rt, t):
+        assert a.shape == b.shape and (a == b).all(), name
+    if tau == 0.004:
+        assert len(t[0]) > 65536                                     # three radix passes
+
+
 @pytest.mark.parametrize("tau", [0.0849, 0.0814, 0.0881])
 def test_far_cell_collision(tau):
     """kernel.cu:460-501: ANY scene key equal to a model key votes -- also the key of a feature cell whose distance
