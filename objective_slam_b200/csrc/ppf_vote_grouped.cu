@@ -243,6 +243,9 @@ __device__ __forceinline__ void vote_grouped(const VoteCtx &ctx, const GroupCtx 
 // ATOMS are 32 adjacent entries here (random bins: ~1.8 wavefronts against 1.1 in the staged loop, where 32 hits share
 // an entry), which is why pieces of 32 keep the staged loop (tools/microbench: 14.2 votes/clk/SM staged at 32 hits
 // against 10.9 here; 9.9 / 7.9 here at 8 / 4 hits against 9.2 / ~6 staged, before the staging cost).
+#ifndef PPF_REST_LONG_E
+#define PPF_REST_LONG_E 8
+#endif
 #ifndef PPF_REST_MIN
 #define PPF_REST_MIN 3
 #endif
@@ -804,11 +807,11 @@ int vote_grouped_launch(VoteArgs a, int ref_count) {
     // entries per lane of vote_rest by the average bucket slice per chunk (see vote_rest)
     const bool long_slices = a.rest_long != 0;
     if (long_slices) {
-        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        vote_kernel_grouped<kGThreads, false, 8><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
+        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false, PPF_REST_LONG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true, PPF_REST_LONG_E>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        vote_kernel_grouped<kGThreads, false, PPF_REST_LONG_E><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
         // reference points whose hits did not fit the queue (none on sparse scenes: the kernel then exits at once)
-        vote_kernel_grouped<kGThreads, true, 8><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
+        vote_kernel_grouped<kGThreads, true, PPF_REST_LONG_E><<<(unsigned)grid, kGThreads, smem, cur_stream()>>>(a);
     } else {
         PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         PPF_CUDA_TRY(cudaFuncSetAttribute(vote_kernel_grouped<kGThreads, true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
