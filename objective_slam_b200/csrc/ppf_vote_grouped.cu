@@ -656,7 +656,18 @@ __global__ void __launch_bounds__(THREADS) vote_kernel_grouped(const VoteArgs a)
         int seg = -1;
         if constexpr (!SEGMENTS) {
             // ---- first pass: all hits of the reference point, whatever the chunk
-            for (uint32_t base0 = 0; base0 < (uint32_t)a.ns; base0 += kGTile) collect_tile(base0);
+            // (every 4 tiles: stop as soon as the queue has overflowed -- on a dense scene every reference point does,
+            // after a fraction of the scene, and the dense-point kernel collects it again anyway.  Block-uniform: the
+            // count is read between two barriers.)
+            for (uint32_t base0 = 0, k = 0; base0 < (uint32_t)a.ns; base0 += kGTile, k++) {
+                collect_tile(base0);
+                if ((k & 3u) == 3u) {
+                    __syncthreads();
+                    const uint32_t have = s_nhits;
+                    __syncthreads();
+                    if (have > Q) break;
+                }
+            }
             __syncthreads();
             n = s_nhits;
             if (n > Q) {
